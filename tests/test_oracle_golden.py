@@ -1,0 +1,165 @@
+"""CPU: the oracle restatement (oracle/svgp_mixture.py) against the golden vectors produced by running
+the reference's own MixtureGPs code on the TF/GPflow shim (tests/golden/make_golden.py), the analytic
+known-answer ELBO, invariants from SURVEY.md §4, and float64 finite differences."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import svgp_mixture as O
+from tests.helpers import RTOL, golden_names, grad_keys, load_golden, relerr
+
+NAMES = golden_names()
+
+
+def _layers(case):
+    return O.layer_from_numpy(case["pred"]), O.layer_from_numpy(case["assign"])
+
+
+def _tv(x):
+    return None if x is None else O.as_t(x)
+
+
+def test_golden_files_present():
+    assert len(NAMES) >= 13, NAMES
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_elbo_and_grads_match_reference_run(name):
+    case, g = load_golden(name)
+    pred, assign = _layers(case)
+    val, grads = O.elbo_and_grads(case["model"], case["lik"], pred, assign, _tv(case["lik_var"]),
+                                  _tv(case["assign_lik_var"]), g["X"], g["Y"], g["z"], g["u"], case["num_data"])
+    assert abs(val - float(g["out.elbo"])) <= RTOL * abs(float(g["out.elbo"])), (val, float(g["out.elbo"]))
+    for k in grad_keys(g):
+        ref = g["out.grad." + k]
+        mine = grads[k].reshape(ref.shape)
+        if np.max(np.abs(ref)) < 1e-12:       # structurally-zero gradients at the init state
+            assert np.max(np.abs(mine)) < 1e-12, k
+        else:
+            assert relerr(mine, ref) <= RTOL, (k, relerr(mine, ref), float(g["cond.pred"]), float(g["cond.assign"]))
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_predictions_match_reference_run(name):
+    case, g = load_golden(name)
+    pred, assign = _layers(case)
+    with torch.no_grad():
+        for lname, layer in (("pred", pred), ("assign", assign)):
+            fm, fv = O.conditional(O.as_t(g["Xtest"]), layer)
+            assert relerr(fm.numpy(), g[f"out.predict_f.{lname}.mean"]) <= RTOL
+            assert relerr(fv.numpy(), g[f"out.predict_f.{lname}.var"]) <= RTOL
+        my, vy = O.predict_y(pred, case["lik"], _tv(case["lik_var"]), g["Xtest"])
+        assert relerr(my.numpy(), g["out.predict_y.mean"]) <= RTOL
+        assert relerr(vy.numpy(), g["out.predict_y.var"]) <= RTOL
+        probs, am = O.predict_assign(assign, g["Xtest"])
+        assert relerr(probs.numpy(), g["out.predict_assign.probs"]) <= RTOL
+        assert np.array_equal(am.numpy(), g["out.predict_assign.argmax"])      # integer argmax: bit-exact
+        assert np.allclose(probs.sum(1).numpy(), 1.0, atol=1e-14)              # rows sum to 1 (models.py:88)
+        if "out.predict_samples.y" in g:
+            sy, sf = O.predict_samples(pred, assign, case["lik"], _tv(case["lik_var"]), g["Xtest"],
+                                       g["sample.z_assign"], g["sample.u"], g["sample.z_pred"])
+            assert relerr(sy.numpy(), g["out.predict_samples.y"]) <= RTOL
+            assert relerr(sf.numpy(), g["out.predict_samples.f"]) <= RTOL
+
+
+def test_known_answer_elbo_at_gpflow_default_init():
+    """at q_mu=0, q_sqrt=I the ELBO of demo_tf2 over the full 1500 points is independent of
+    the noise and of S: mean_n[-1/2 log 2pi - 1/2 log s - 1/2 (y^2 + sf2)/s] = -2.8367259694802307."""
+    case, g = load_golden("demo_tf2_full.init")
+    Y = g["Y"]
+    s, sf2 = 0.5, 0.5
+    analytic = float(np.mean(-0.5 * math.log(2 * math.pi) - 0.5 * math.log(s) - 0.5 * (Y ** 2 + sf2) / s))
+    assert abs(analytic - (-2.8367259694802307)) < 1e-14
+    assert abs(float(g["out.elbo"]) - analytic) < 1e-13        # the reference run on the shim
+    pred, assign = _layers(case)
+    for seed, S in ((0, 1), (1, 4)):
+        rng = np.random.default_rng(seed)
+        z = rng.standard_normal((S, 1500, 3))
+        u = rng.uniform(np.finfo(np.float64).tiny, 1, (S, 1500, 3))
+        with torch.no_grad():
+            val = float(O.elbo("SMGP", "gaussian", pred, assign, _tv(case["lik_var"]), None, g["X"], Y, z, u, 1500.0))
+        assert abs(val - analytic) < 1e-13, (S, val)
+
+
+def test_elbo_is_a_per_point_mean_and_kl_scales_with_num_data():
+    case, g = load_golden("synth4_small.pert")
+    pred, assign = _layers(case)
+    X, Y, z, u = g["X"], g["Y"], g["z"], g["u"]
+    args = ("SMGP", "gaussian", pred, assign, _tv(case["lik_var"]), None)
+    with torch.no_grad():
+        e1 = float(O.elbo(*args, X, Y, z, u, 1000.0))
+        e2 = float(O.elbo(*args, np.concatenate([X, X]), np.concatenate([Y, Y]), np.concatenate([z, z], 1),
+                          np.concatenate([u, u], 1), 1000.0))
+        kl = float(O.gauss_kl_white(pred) + O.gauss_kl_white(assign))
+        e3 = float(O.elbo(*args, X, Y, z, u, 500.0))
+    assert abs(e1 - e2) < 1e-12 * abs(e1)                      # duplicating the batch leaves the mean unchanged
+    assert abs((e1 - e3) - kl * (1 / 500.0 - 1 / 1000.0)) < 1e-12 * abs(e1)
+
+
+def test_data_parallel_split_invariance():
+    """shard sums (divided by the GLOBAL N) add up to the single-device value, for the
+    ELBO and for every gradient; the KL term is added by one shard only."""
+    case, g = load_golden("synth4_small.pert")
+    pred, assign = _layers(case)
+    X, Y, z, u = g["X"], g["Y"], g["z"], g["u"]
+    N = X.shape[0]
+    full, gfull = O.elbo_and_grads("SMGP", "gaussian", pred, assign, _tv(case["lik_var"]), None, X, Y, z, u,
+                                   case["num_data"])
+    tot, gtot = 0.0, None
+    for r, sl in enumerate((slice(0, N // 2), slice(N // 2, N))):
+        v, gr = O.elbo_and_grads("SMGP", "gaussian", pred, assign, _tv(case["lik_var"]), None, X[sl], Y[sl],
+                                 z[:, sl], u[:, sl], case["num_data"] if r == 0 else math.inf, n_total=N)
+        tot += v
+        gtot = gr if gtot is None else {k: gtot[k] + gr[k] for k in gr}
+    assert abs(tot - full) < 1e-12 * abs(full)
+    for k in gfull:
+        assert relerr(gtot[k], gfull[k]) < 1e-10, k
+
+
+def test_multiclass_term_is_independent_of_W():
+    """with MultiClass experts the [S,N,1] expectation times W summed over k is a no-op."""
+    case, g = load_golden("demo_tf2_2d_modified_multiclass.pert")
+    pred, _ = _layers(case)
+    with torch.no_grad():
+        mu, var = O.conditional(O.as_t(g["X"]), pred)
+        ve = O.multiclass_ve(O.as_t(g["Y"]), mu, var)
+        W = torch.softmax(torch.randn(5, mu.shape[0], 2, dtype=torch.float64), -1)
+        t = (ve[None, :, None] * W).sum(2)
+    assert relerr(t.numpy(), ve[None].expand(5, -1).numpy()) < 1e-14
+
+
+def test_gradients_against_central_finite_differences():
+    case, g = load_golden("smgpmod_gauss_small.pert")
+    pred, assign = _layers(case)
+    common = dict(X=g["X"], Y=g["Y"], z=g["z"], u=g["u"], num_data=case["num_data"])
+    _, grads = O.elbo_and_grads(case["model"], case["lik"], pred, assign, _tv(case["lik_var"]),
+                                _tv(case["assign_lik_var"]), **common)
+
+    def f(p, a, lv, alv):
+        with torch.no_grad():
+            return float(O.elbo(case["model"], case["lik"], p, a, lv, alv, **common))
+
+    rng = np.random.default_rng(0)
+    # T=0.01 Gumbel-softmax makes the ELBO stiff in the assign layer: use tiny steps and loose tolerance there
+    for lname, key, h, tol in (("pred", "q_mu", 1e-6, 1e-6), ("pred", "Z", 1e-6, 1e-5), ("pred", "variance", 1e-6, 1e-6),
+                               ("pred", "q_sqrt", 1e-6, 1e-6), ("assign", "q_mu", 1e-7, 1e-3),
+                               ("assign", "lengthscales", 1e-7, 1e-3)):
+        base = {"pred": pred, "assign": assign}
+        t = base[lname][key]
+        if key == "q_sqrt":
+            idx = (1, 5, 3)
+        elif t.dim() == 0:
+            idx = ()
+        else:
+            idx = tuple(int(rng.integers(0, s)) for s in t.shape)
+        vals = []
+        for sgn in (+1, -1):
+            layer = {k: v.clone() for k, v in base[lname].items()}
+            layer[key][idx] += sgn * h
+            p, a = (layer, assign) if lname == "pred" else (pred, layer)
+            vals.append(f(p, a, _tv(case["lik_var"]), _tv(case["assign_lik_var"])))
+        fd = (vals[0] - vals[1]) / (2 * h)
+        an = float(grads[f"{lname}.{key}"][idx])
+        assert abs(fd - an) <= tol * max(1.0, abs(an)), (lname, key, fd, an)

@@ -1,0 +1,153 @@
+/* libmgp — C-ABI of the B200-native SVGP-mixture (data-association GP) hot path.
+ *
+ * The reference (LouieMiddle/ModulatedGPs) has no FFI: its boundary is the Python class API of the
+ * MixtureGPs package.  Each entry point below replaces the arithmetic behind one of those methods
+ * (reference file:line cited per function); modulatedgps_b200/ binds them with ctypes and re-exposes the
+ * reference's class names.  See INTEGRATION.md for the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to float64 (or int64 where stated), row-major, contiguous,
+ *     caller-owned; the library never frees or retains caller memory beyond the call;
+ *   - all work is enqueued on the stream given to mgp_ctx_create; calls are asynchronous with respect to
+ *     the host unless stated; one ctx per (process, device); a ctx is not thread-safe;
+ *   - every function returns 0 on success, non-zero (MGP_ERR_*) on failure; mgp_last_error(ctx) gives text;
+ *     no exception or abort crosses this boundary.  There is NO CPU fallback: without a CUDA device
+ *     mgp_ctx_create fails.
+ */
+#ifndef MGP_H_
+#define MGP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGP_OK 0
+#define MGP_ERR_BAD_ARG 1
+#define MGP_ERR_CUDA 2
+#define MGP_ERR_NOT_PD 3   /* Cholesky of Kuu hit a non-positive pivot (TF: InvalidArgumentError) */
+#define MGP_ERR_NOMEM 4
+
+#define MGP_MAX_K 8        /* latent GPs (components) per layer */
+#define MGP_MAX_D 32       /* input dimensions */
+
+#define MGP_MODEL_SMGP 0          /* MixtureGPs/models.py:44-103  */
+#define MGP_MODEL_SMGP_MODIFIED 1 /* MixtureGPs/models.py:106-123 */
+#define MGP_LIK_GAUSSIAN 0        /* MixtureGPs/likelihoods.py:12-41 (GaussianModified) */
+#define MGP_LIK_MULTICLASS 1      /* gpflow MultiClass(RobustMax), via broadcasting_lik.py:26-37 */
+
+typedef struct mgp_ctx mgp_ctx;
+
+/* One whitened SVGP layer (SVGPModified, MixtureGPs/models.py:147-160), CONSTRAINED parameter values. */
+typedef struct {
+    int32_t M, D, K;             /* inducing points, input dims, latent GPs */
+    int32_t n_lengthscales;      /* 1 (isotropic, every demo) or D (ARD) */
+    const double* Z;             /* [M, D]   inducing_variable.Z */
+    const double* q_mu;          /* [M, K] */
+    const double* q_sqrt;        /* [K, M, M] dense; only the lower triangle is read (band_part(-1,0)) */
+    const double* variance;      /* [1]  kernel.variance */
+    const double* lengthscales;  /* [n_lengthscales] */
+} mgp_layer;
+
+/* Gradient of the ELBO w.r.t. the constrained values of one layer; same shapes as mgp_layer.
+ * q_sqrt gradient is dense [K, M, M] with zeros above the diagonal. */
+typedef struct {
+    double* Z;
+    double* q_mu;
+    double* q_sqrt;
+    double* variance;
+    double* lengthscales;
+} mgp_layer_grad;
+
+/* Noise for the Monte-Carlo pass.  Parity mode: explicit arrays (what tf.random.normal, models.py:57, and
+ * TFP's uniform draw, models.py:73, would have returned).  Throughput mode: z = u = NULL and a Philox
+ * counter-based stream keyed by (seed, global point index, sample, component), independent of sharding. */
+typedef struct {
+    const double* z;        /* [S, N_local, K] standard normal, or NULL */
+    const double* u;        /* [S, N_local, K] uniform on (DBL_MIN, 1), or NULL */
+    uint64_t seed;          /* Philox key when z/u are NULL */
+    int64_t point_offset;   /* global index of this shard's first point (Philox counter offset) */
+} mgp_noise;
+
+typedef struct {
+    int32_t model;            /* MGP_MODEL_* */
+    int32_t lik;              /* MGP_LIK_*: the EXPERT likelihood (pred layer) */
+    int32_t S;                /* num_samples */
+    int32_t reserved;
+    double temperature;       /* 1e-2 in the reference (models.py:60) */
+    double num_data;          /* SGP.num_data: divisor of the KL term (models.py:79) */
+    int64_t n_global;         /* global minibatch size: divisor of the per-point mean (models.py:76) */
+} mgp_elbo_cfg;
+
+int mgp_ctx_create(int device, void* cuda_stream, mgp_ctx** out);
+void mgp_ctx_destroy(mgp_ctx* ctx);
+const char* mgp_last_error(const mgp_ctx* ctx);
+/* number of CUDA kernels this ctx has launched since creation (bench.py's gpu_launches) */
+int64_t mgp_launch_count(const mgp_ctx* ctx);
+/* Synchronises the stream and reports deferred device-side failures (MGP_ERR_NOT_PD when a Cholesky pivot
+ * was not positive since the last check; MGP_ERR_CUDA for asynchronous CUDA errors). */
+int mgp_check_status(mgp_ctx* ctx);
+/* cap for the per-call point chunk (0 = automatic: whole shard if the materialised A fits the budget) */
+int mgp_set_chunk_points(mgp_ctx* ctx, int64_t max_points);
+
+/* SVGPModified.predict_f(Xnew, full_cov=False)  — MixtureGPs/models.py:129-144 (one of the S identical
+ * slices the reference returns).  X [N, D] -> fmean [N, K], fvar [N, K]. */
+int mgp_svgp_predict_f(mgp_ctx* ctx, const mgp_layer* layer, const double* X, int64_t N,
+                       double* fmean, double* fvar);
+
+/* SVGP.prior_kl() with whiten=True — gpflow gauss_kl(q_mu, q_sqrt, None), call site models.py:79.  kl [1]. */
+int mgp_prior_kl(mgp_ctx* ctx, const mgp_layer* layer, double* kl);
+
+/* SGP.predict_y — models.py:38-41 + likelihoods.py:31-32 (Gaussian: Fvar + variance_k) or gpflow
+ * MultiClass._predict_mean_and_var.  lik_var [K] (ignored for MULTICLASS). */
+int mgp_predict_y(mgp_ctx* ctx, const mgp_layer* pred, int32_t lik, const double* lik_var,
+                  const double* X, int64_t N, double* mean, double* var);
+
+/* SMGP.predict_assign — models.py:85-89: probs [N, K] = softmax_K(mu_assign); argmax int64 [N]
+ * (lowest index wins ties, as np.argmax / tf.argmax). */
+int mgp_predict_assign(mgp_ctx* ctx, const mgp_layer* assign, const double* X, int64_t N,
+                       double* probs, int64_t* argmax);
+
+/* SMGP.predict_samples — models.py:91-103.  noise->z is the z of W_dist (models.py:57), noise->u the relaxed
+ * one-hot uniform, z_pred [S, N, K] the second normal draw (models.py:98).  Outputs [S, N] each. */
+int mgp_predict_samples(mgp_ctx* ctx, const mgp_layer* pred, const mgp_layer* assign, int32_t lik,
+                        const double* lik_var, const double* X, int64_t N, int32_t S, double temperature,
+                        const mgp_noise* noise, const double* z_pred, double* samples_y, double* samples_f);
+
+/* Size (in doubles) of the flat reduction buffer of mgp_elbo_local for these layers. */
+int64_t mgp_reduce_buffer_len(const mgp_layer* pred, const mgp_layer* assign);
+
+/* ELBO forward + backward, phase 1 (per shard): SMGP._build_likelihood / SMGPModified.E_log_p_Y —
+ * models.py:55-79,112-123 — and TF's reverse pass through it (utils/training_utils.py:8-10), up to the
+ * point where every per-shard quantity is a SUM over this shard's points.  Writes those sums to
+ * `reduce_buf` (mgp_reduce_buffer_len doubles): this is the single buffer a data-parallel caller
+ * all-reduces (sum) across ranks.  X [N_local, D], Y [N_local]. */
+int mgp_elbo_local(mgp_ctx* ctx, const mgp_elbo_cfg* cfg, const mgp_layer* pred, const mgp_layer* assign,
+                   const double* lik_var, const double* assign_lik_var,
+                   const double* X, const double* Y, int64_t N_local, const mgp_noise* noise,
+                   double* reduce_buf);
+
+/* Phase 2 (replicated): from the (all-reduced) buffer, the KL terms (models.py:79), the Cholesky and
+ * kernel backward, and the final gradients w.r.t. constrained values.  elbo [1]; lik_var_grad [K] and
+ * assign_lik_var_grad [K] may be NULL when the corresponding likelihood has no variance. */
+int mgp_elbo_finish(mgp_ctx* ctx, const mgp_elbo_cfg* cfg, const mgp_layer* pred, const mgp_layer* assign,
+                    const double* lik_var, const double* assign_lik_var, const double* reduce_buf,
+                    double* elbo, mgp_layer_grad* pred_grad, mgp_layer_grad* assign_grad,
+                    double* lik_var_grad, double* assign_lik_var_grad);
+
+/* Convenience: phase 1 + phase 2 on one device (no exchange). */
+int mgp_elbo_fwd_bwd(mgp_ctx* ctx, const mgp_elbo_cfg* cfg, const mgp_layer* pred, const mgp_layer* assign,
+                     const double* lik_var, const double* assign_lik_var,
+                     const double* X, const double* Y, int64_t N_local, const mgp_noise* noise,
+                     double* elbo, mgp_layer_grad* pred_grad, mgp_layer_grad* assign_grad,
+                     double* lik_var_grad, double* assign_lik_var_grad);
+
+/* Stage-level entry points (used by the parity tests to localise a failure; same kernels as above).
+ * L, Linv: [M, M] row-major lower-triangular outputs for one layer. */
+int mgp_debug_kuu_chol(mgp_ctx* ctx, const mgp_layer* layer, double* Kuu, double* L, double* Linv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGP_H_ */

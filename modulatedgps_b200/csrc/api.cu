@@ -1,0 +1,540 @@
+// libmgp C-ABI (include/mgp.h): context, workspace and the orchestration of the kernels.
+// No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mgp.h"
+#include "kernels.h"
+
+using namespace mgp;
+
+static inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+namespace {
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct LayerSlot {
+    LayerDev dev{};
+    Buf inv_ls, Zs_rm, Zs_fm, zs2, Kuu, L, Linv, W_Linv, W_LinvT, Lq_rm, W_LqT, Q_rm, W_Q, W_mT, T1, T2, T3, Sfull, rowout;
+    Buf A, asq, fmean, fvar, mubar, vbar;   // chunk buffers
+    Buf syrk_part, mraw_part, esum_part;    // per-CTA partial sums
+    int nsplit = 0, mraw_nparts = 0, esum_nparts = 0;
+};
+
+}  // namespace
+
+struct mgp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    size_t total_mem = 0;
+    int64_t launches = 0;
+    int64_t chunk_cap = 0;
+    std::string err;
+    LayerSlot slot[2];
+    Buf mc_part, scratch_rb, kl, status;
+    bool pre_valid = false;
+    std::vector<void*> owned;
+};
+
+namespace {
+
+int fail(mgp_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+int cuda_fail(mgp_ctx* c, cudaError_t e, const char* where) {
+    return fail(c, MGP_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+
+#define CUDA_TRY(ctx, expr)                                          \
+    do {                                                             \
+        cudaError_t e__ = (expr);                                    \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #expr);   \
+    } while (0)
+
+int ensure(mgp_ctx* c, Buf& b, size_t bytes, bool zero = false) {
+    if (bytes == 0) bytes = 8;
+    if (b.cap >= bytes) return MGP_OK;
+    if (b.p) {
+        // stream-ordered with respect to our own work: wait before freeing
+        cudaStreamSynchronize(c->stream);
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    const size_t want = (bytes + 255) / 256 * 256;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, MGP_ERR_NOMEM, "cudaMalloc of " + std::to_string(want) + " bytes failed: " + cudaGetErrorString(e));
+    }
+    b.cap = want;
+    if (zero) cudaMemsetAsync(b.p, 0, want, c->stream);
+    return MGP_OK;
+}
+
+#define TRY(expr)                     \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != MGP_OK) return rc__; \
+    } while (0)
+
+int check_layer(mgp_ctx* c, const mgp_layer* l) {
+    if (!l) return fail(c, MGP_ERR_BAD_ARG, "layer is NULL");
+    if (l->M < 1 || l->D < 1 || l->K < 1) return fail(c, MGP_ERR_BAD_ARG, "layer: M, D, K must be positive");
+    if (l->K > MGP_MAX_K) return fail(c, MGP_ERR_BAD_ARG, "layer: K exceeds MGP_MAX_K (8)");
+    if (l->D > MGP_MAX_D) return fail(c, MGP_ERR_BAD_ARG, "layer: D exceeds MGP_MAX_D (32)");
+    if (l->n_lengthscales != 1 && l->n_lengthscales != l->D)
+        return fail(c, MGP_ERR_BAD_ARG, "layer: n_lengthscales must be 1 or D");
+    if (!l->Z || !l->q_mu || !l->q_sqrt || !l->variance || !l->lengthscales)
+        return fail(c, MGP_ERR_BAD_ARG, "layer: NULL parameter pointer");
+    const int Mp = (l->M + 31) / 32 * 32;
+    if ((size_t)Mp * 20 * 8 + 16 * 1024 > 227 * 1024)
+        return fail(c, MGP_ERR_BAD_ARG, "layer: M too large for the shared-memory tile (M <= 1312)");
+    return MGP_OK;
+}
+
+// fill slot.dev for this layer and size its per-layer buffers
+int setup_layer(mgp_ctx* c, LayerSlot& s, const mgp_layer* l, bool need_bwd) {
+    TRY(check_layer(c, l));
+    LayerDev& d = s.dev;
+    d.M = l->M; d.D = l->D; d.K = l->K; d.n_ls = l->n_lengthscales;
+    d.Mp = (l->M + 31) / 32 * 32;
+    d.Dp = (l->D + 3) / 4 * 4;
+    d.Z = l->Z; d.q_mu = l->q_mu; d.q_sqrt = l->q_sqrt; d.variance = l->variance; d.lengthscales = l->lengthscales;
+    const size_t Mp = d.Mp, Dp = d.Dp, K = d.K, mm = Mp * Mp * sizeof(double);
+    TRY(ensure(c, s.inv_ls, Dp * 8));
+    TRY(ensure(c, s.Zs_rm, Mp * Dp * 8));
+    TRY(ensure(c, s.Zs_fm, Mp * Dp * 8));
+    TRY(ensure(c, s.zs2, Mp * 8));
+    TRY(ensure(c, s.Kuu, mm));
+    TRY(ensure(c, s.L, mm));
+    TRY(ensure(c, s.Linv, mm));
+    TRY(ensure(c, s.W_Linv, mm));
+    TRY(ensure(c, s.W_LinvT, mm));
+    TRY(ensure(c, s.Lq_rm, K * mm));
+    TRY(ensure(c, s.W_LqT, K * mm));
+    TRY(ensure(c, s.W_mT, 16 * Mp * 8));
+    d.inv_ls = (double*)s.inv_ls.p; d.Zs_rm = (double*)s.Zs_rm.p; d.Zs_fm = (double*)s.Zs_fm.p; d.zs2 = (double*)s.zs2.p;
+    d.Kuu = (double*)s.Kuu.p; d.L = (double*)s.L.p; d.Linv = (double*)s.Linv.p;
+    d.W_Linv = (double*)s.W_Linv.p; d.W_LinvT = (double*)s.W_LinvT.p;
+    d.Lq_rm = (double*)s.Lq_rm.p; d.W_LqT = (double*)s.W_LqT.p; d.W_mT = (double*)s.W_mT.p;
+    if (need_bwd) {
+        TRY(ensure(c, s.Q_rm, K * mm));
+        TRY(ensure(c, s.W_Q, Mp * (K * Mp + KP) * 8));
+        TRY(ensure(c, s.T1, K * mm));
+        TRY(ensure(c, s.T2, mm));
+        TRY(ensure(c, s.T3, mm));
+        TRY(ensure(c, s.Sfull, K * mm));
+        TRY(ensure(c, s.rowout, Mp * (2 * Dp + 1) * 8));
+        d.Q_rm = (double*)s.Q_rm.p; d.W_Q = (double*)s.W_Q.p; d.T1 = (double*)s.T1.p; d.T2 = (double*)s.T2.p;
+        d.T3 = (double*)s.T3.p; d.Sfull = (double*)s.Sfull.p; d.rowout = (double*)s.rowout.p;
+    } else {
+        // forward-only paths still use T1 as scratch of nothing; keep pointers null-safe
+        d.Q_rm = d.W_Q = d.T1 = d.T2 = d.T3 = d.Sfull = d.rowout = nullptr;
+    }
+    return MGP_OK;
+}
+
+int ensure_chunk(mgp_ctx* c, LayerSlot& s, int64_t ldn, bool need_bwd) {
+    const size_t Mp = s.dev.Mp, K = s.dev.K;
+    TRY(ensure(c, s.A, Mp * (size_t)ldn * 8, true));
+    TRY(ensure(c, s.asq, (size_t)ldn * 8, true));
+    TRY(ensure(c, s.fmean, (size_t)ldn * K * 8, true));
+    TRY(ensure(c, s.fvar, (size_t)ldn * K * 8, true));
+    if (need_bwd) {
+        TRY(ensure(c, s.mubar, (size_t)ldn * K * 8, true));
+        TRY(ensure(c, s.vbar, (size_t)ldn * K * 8, true));
+    }
+    return MGP_OK;
+}
+
+ChunkBuffers chunk_of(const LayerSlot& s, const double* X, int64_t n, int64_t ldn) {
+    ChunkBuffers cb;
+    cb.n = n; cb.ldn = ldn; cb.X = X;
+    cb.A = (double*)s.A.p; cb.asq = (double*)s.asq.p; cb.fmean = (double*)s.fmean.p; cb.fvar = (double*)s.fvar.p;
+    cb.mubar = (double*)s.mubar.p; cb.vbar = (double*)s.vbar.p;
+    return cb;
+}
+
+Launch launch_of(mgp_ctx* c) { return Launch{c->stream, &c->launches, c->num_sms}; }
+
+// points per chunk so that the materialised A of `nlayers` layers fits the budget
+int64_t pick_chunk(mgp_ctx* c, int64_t N, int Mp_max, int nlayers) {
+    int64_t cap = c->chunk_cap;
+    if (cap <= 0) {
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        double budget = fmin(0.4 * (double)c->total_mem, 0.7 * (double)free_b);
+        for (int i = 0; i < 2; ++i) budget += (double)c->slot[i].A.cap;   // what we already hold counts as available
+        cap = (int64_t)(budget / ((double)nlayers * (Mp_max + 6 * MGP_MAX_K) * 8.0));
+        if (cap < 4096) cap = 4096;
+    }
+    cap = cap / 64 * 64;
+    if (cap < 64) cap = 64;
+    return N < cap ? N : cap;
+}
+
+__global__ void elbo_finalize_kernel(const double* rb, const double* kl, double num_data, int K, double* elbo,
+                                     double* glik, double* galik) {
+    if (threadIdx.x == 0) elbo[0] = rb[RB_DATA] - (kl[0] + kl[1]) / num_data;
+    if (threadIdx.x < K) {
+        if (glik) glik[threadIdx.x] = rb[RB_LIKVAR + threadIdx.x];
+        if (galik) galik[threadIdx.x] = rb[RB_ALIKVAR + threadIdx.x];
+    }
+}
+
+int check_cfg(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, const mgp_layer* assign,
+              const double* lik_var, const double* assign_lik_var) {
+    if (!cfg) return fail(c, MGP_ERR_BAD_ARG, "cfg is NULL");
+    if (cfg->model != MGP_MODEL_SMGP && cfg->model != MGP_MODEL_SMGP_MODIFIED) return fail(c, MGP_ERR_BAD_ARG, "cfg.model");
+    if (cfg->lik != MGP_LIK_GAUSSIAN && cfg->lik != MGP_LIK_MULTICLASS) return fail(c, MGP_ERR_BAD_ARG, "cfg.lik");
+    if (cfg->S < 1) return fail(c, MGP_ERR_BAD_ARG, "cfg.S must be >= 1");
+    if (!(cfg->temperature > 0.0)) return fail(c, MGP_ERR_BAD_ARG, "cfg.temperature must be > 0");
+    if (!(cfg->num_data > 0.0)) return fail(c, MGP_ERR_BAD_ARG, "cfg.num_data must be > 0");
+    if (cfg->n_global < 1) return fail(c, MGP_ERR_BAD_ARG, "cfg.n_global must be >= 1");
+    TRY(check_layer(c, pred));
+    TRY(check_layer(c, assign));
+    if (pred->K != assign->K || pred->D != assign->D) return fail(c, MGP_ERR_BAD_ARG, "pred/assign layers disagree on K or D");
+    if (cfg->lik == MGP_LIK_GAUSSIAN && !lik_var) return fail(c, MGP_ERR_BAD_ARG, "Gaussian expert likelihood needs lik_var");
+    if (cfg->lik == MGP_LIK_MULTICLASS && pred->K < 2) return fail(c, MGP_ERR_BAD_ARG, "MultiClass needs K >= 2");
+    if (cfg->model == MGP_MODEL_SMGP_MODIFIED && !assign_lik_var)
+        return fail(c, MGP_ERR_BAD_ARG, "SMGPModified needs assign_lik_var");
+    return MGP_OK;
+}
+
+// forward conditional of one layer over [N, D] points into caller arrays (n*K doubles each)
+int run_predict_f(mgp_ctx* c, LayerSlot& s, const double* X, int64_t N, double* fmean, double* fvar) {
+    const Launch ln = launch_of(c);
+    const int K = s.dev.K, D = s.dev.D;
+    const int64_t Nc = pick_chunk(c, N, s.dev.Mp, 1);
+    const int64_t ldn = round_up64(Nc, 64);
+    TRY(ensure_chunk(c, s, ldn, false));
+    for (int64_t c0 = 0; c0 < N; c0 += Nc) {
+        const int64_t n = (N - c0 < Nc) ? N - c0 : Nc;
+        ChunkBuffers cb = chunk_of(s, X + c0 * D, n, ldn);
+        cond_fwd_a(s.dev, cb, ln);
+        cond_fwd_b(s.dev, cb, ln);
+        CUDA_TRY(c, cudaMemcpyAsync(fmean + c0 * K, cb.fmean, sizeof(double) * n * K, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(fvar + c0 * K, cb.fvar, sizeof(double) * n * K, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return MGP_OK;
+}
+
+}  // namespace
+
+// ====================================================================================================
+extern "C" {
+
+int mgp_ctx_create(int device, void* cuda_stream, mgp_ctx** out) {
+    if (!out) return MGP_ERR_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) return MGP_ERR_CUDA;   // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return MGP_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MGP_ERR_CUDA;
+    mgp_ctx* c = new mgp_ctx();
+    c->device = device;
+    c->stream = (cudaStream_t)cuda_stream;
+    c->num_sms = prop.multiProcessorCount;
+    c->total_mem = prop.totalGlobalMem;
+    if (ensure(c, c->kl, 64) != MGP_OK || ensure(c, c->status, 64, true) != MGP_OK) {
+        delete c;
+        return MGP_ERR_NOMEM;
+    }
+    *out = c;
+    return MGP_OK;
+}
+
+void mgp_ctx_destroy(mgp_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    auto rel = [](Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; };
+    for (auto& s : c->slot) {
+        Buf* all[] = {&s.inv_ls, &s.Zs_rm, &s.Zs_fm, &s.zs2, &s.Kuu, &s.L, &s.Linv, &s.W_Linv, &s.W_LinvT, &s.Lq_rm,
+                      &s.W_LqT, &s.Q_rm, &s.W_Q, &s.W_mT, &s.T1, &s.T2, &s.T3, &s.Sfull, &s.rowout, &s.A, &s.asq,
+                      &s.fmean, &s.fvar, &s.mubar, &s.vbar, &s.syrk_part, &s.mraw_part, &s.esum_part};
+        for (Buf* b : all) rel(*b);
+    }
+    rel(c->mc_part); rel(c->scratch_rb); rel(c->kl); rel(c->status);
+    delete c;
+}
+
+const char* mgp_last_error(const mgp_ctx* c) { return c ? c->err.c_str() : "mgp: NULL context (no CUDA device?)"; }
+
+int64_t mgp_launch_count(const mgp_ctx* c) { return c ? c->launches : 0; }
+
+int mgp_set_chunk_points(mgp_ctx* c, int64_t max_points) {
+    if (!c || max_points < 0) return MGP_ERR_BAD_ARG;
+    c->chunk_cap = max_points;
+    return MGP_OK;
+}
+
+int mgp_check_status(mgp_ctx* c) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    int h = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&h, c->status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    if (h & 1) {
+        cudaMemsetAsync(c->status.p, 0, sizeof(int), c->stream);
+        return fail(c, MGP_ERR_NOT_PD, "Cholesky of Kuu + jitter I failed: matrix is not positive definite");
+    }
+    return MGP_OK;
+}
+
+int mgp_svgp_predict_f(mgp_ctx* c, const mgp_layer* layer, const double* X, int64_t N, double* fmean, double* fvar) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    if (N < 0 || (N > 0 && (!X || !fmean || !fvar))) return fail(c, MGP_ERR_BAD_ARG, "predict_f: bad arguments");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->pre_valid = false;
+    TRY(setup_layer(c, c->slot[0], layer, false));
+    if (N == 0) return MGP_OK;
+    precompute_layer(c->slot[0].dev, false, (int*)c->status.p, launch_of(c));
+    TRY(run_predict_f(c, c->slot[0], X, N, fmean, fvar));
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
+int mgp_prior_kl(mgp_ctx* c, const mgp_layer* layer, double* kl) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    if (!kl) return fail(c, MGP_ERR_BAD_ARG, "prior_kl: NULL output");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->pre_valid = false;
+    TRY(setup_layer(c, c->slot[0], layer, false));
+    prior_kl_layer(c->slot[0].dev, kl, launch_of(c));
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
+int mgp_predict_y(mgp_ctx* c, const mgp_layer* pred, int32_t lik, const double* lik_var, const double* X, int64_t N,
+                  double* mean, double* var) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    if (lik == MGP_LIK_GAUSSIAN && !lik_var) return fail(c, MGP_ERR_BAD_ARG, "predict_y: Gaussian likelihood needs lik_var");
+    TRY(mgp_svgp_predict_f(c, pred, X, N, mean, var));
+    if (N == 0) return MGP_OK;
+    predict_y_kernel(mean, var, N, pred->K, lik, lik_var, mean, var, launch_of(c));
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
+int mgp_predict_assign(mgp_ctx* c, const mgp_layer* assign, const double* X, int64_t N, double* probs, int64_t* argmax) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    if (N > 0 && (!probs || !argmax)) return fail(c, MGP_ERR_BAD_ARG, "predict_assign: NULL output");
+    if (N == 0) return MGP_OK;
+    TRY(ensure(c, c->scratch_rb, (size_t)N * assign->K * 8));
+    TRY(mgp_svgp_predict_f(c, assign, X, N, probs, (double*)c->scratch_rb.p));
+    predict_assign_kernel(probs, N, assign->K, probs, argmax, launch_of(c));
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
+int mgp_predict_samples(mgp_ctx* c, const mgp_layer* pred, const mgp_layer* assign, int32_t lik, const double* lik_var,
+                        const double* X, int64_t N, int32_t S, double temperature, const mgp_noise* noise,
+                        const double* z_pred, double* samples_y, double* samples_f) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    if (N < 0 || S < 1 || !noise || !(temperature > 0.0)) return fail(c, MGP_ERR_BAD_ARG, "predict_samples: bad arguments");
+    if ((noise->z == nullptr) != (noise->u == nullptr) || (noise->z != nullptr && !z_pred))
+        return fail(c, MGP_ERR_BAD_ARG, "predict_samples: z, u and z_pred must be given together");
+    if (lik == MGP_LIK_GAUSSIAN && !lik_var) return fail(c, MGP_ERR_BAD_ARG, "predict_samples: needs lik_var");
+    if (N == 0) return MGP_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->pre_valid = false;
+    TRY(check_layer(c, pred));
+    TRY(check_layer(c, assign));
+    if (pred->K != assign->K || pred->D != assign->D) return fail(c, MGP_ERR_BAD_ARG, "pred/assign layers disagree on K or D");
+    const int K = pred->K;
+    TRY(ensure(c, c->scratch_rb, (size_t)N * K * 8 * 4));
+    double* fm_p = (double*)c->scratch_rb.p;
+    double *fv_p = fm_p + N * K, *fm_a = fv_p + N * K, *fv_a = fm_a + N * K;
+    const Launch ln = launch_of(c);
+    TRY(setup_layer(c, c->slot[0], pred, false));
+    precompute_layer(c->slot[0].dev, false, (int*)c->status.p, ln);
+    TRY(run_predict_f(c, c->slot[0], X, N, fm_p, fv_p));
+    TRY(setup_layer(c, c->slot[1], assign, false));
+    precompute_layer(c->slot[1].dev, false, (int*)c->status.p, ln);
+    TRY(run_predict_f(c, c->slot[1], X, N, fm_a, fv_a));
+    SampleArgs a;
+    a.S = S; a.K = K; a.lik = lik; a.temperature = temperature; a.n = N;
+    a.fmean_p = fm_p; a.fvar_p = fv_p; a.fmean_a = fm_a; a.fvar_a = fv_a; a.lik_var = lik_var;
+    a.z = noise->z; a.u = noise->u; a.z_pred = z_pred; a.seed = noise->seed; a.point_offset = noise->point_offset;
+    a.samples_y = samples_y; a.samples_f = samples_f;
+    predict_samples_kernel(a, ln);
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
+int64_t mgp_reduce_buffer_len(const mgp_layer* pred, const mgp_layer* assign) {
+    if (!pred || !assign) return 0;
+    const int Mp_p = (pred->M + 31) / 32 * 32, Mp_a = (assign->M + 31) / 32 * 32;
+    const int Dp = (pred->D + 3) / 4 * 4;
+    const LayerRB rp = layer_rb(RB_HEADER, Mp_p, Dp, pred->K);
+    const LayerRB ra = layer_rb(rp.end, Mp_a, Dp, assign->K);
+    return ra.end;
+}
+
+int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, const mgp_layer* assign,
+                   const double* lik_var, const double* assign_lik_var, const double* X, const double* Y,
+                   int64_t N_local, const mgp_noise* noise, double* reduce_buf) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    TRY(check_cfg(c, cfg, pred, assign, lik_var, assign_lik_var));
+    if (N_local < 0 || !noise || !reduce_buf || (N_local > 0 && (!X || !Y)))
+        return fail(c, MGP_ERR_BAD_ARG, "elbo_local: bad arguments");
+    if ((noise->z == nullptr) != (noise->u == nullptr)) return fail(c, MGP_ERR_BAD_ARG, "noise: z and u must be given together");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const Launch ln = launch_of(c);
+    LayerSlot &sp = c->slot[0], &sa = c->slot[1];
+    TRY(setup_layer(c, sp, pred, true));
+    TRY(setup_layer(c, sa, assign, true));
+    const int K = pred->K, D = pred->D;
+    const LayerRB rp = layer_rb(RB_HEADER, sp.dev.Mp, sp.dev.Dp, K);
+    const LayerRB ra = layer_rb(rp.end, sa.dev.Mp, sa.dev.Dp, K);
+    CUDA_TRY(c, cudaMemsetAsync(reduce_buf, 0, sizeof(double) * ra.end, c->stream));
+
+    precompute_layer(sp.dev, true, (int*)c->status.p, ln);
+    precompute_layer(sa.dev, true, (int*)c->status.p, ln);
+    c->pre_valid = true;
+    if (N_local == 0) return MGP_OK;   // an empty shard contributes zeros
+
+    const int Mp_max = sp.dev.Mp > sa.dev.Mp ? sp.dev.Mp : sa.dev.Mp;
+    const int64_t Nc = pick_chunk(c, N_local, Mp_max, 2);
+    const int64_t ldn = round_up64(Nc, 64);
+    TRY(ensure_chunk(c, sp, ldn, true));
+    TRY(ensure_chunk(c, sa, ldn, true));
+    const int maxparts = stream_max_parts(ln);
+    LayerSlot* slots[2] = {&sp, &sa};
+    for (LayerSlot* s : slots) {
+        const size_t Mp = s->dev.Mp, E = 1 + 2 * s->dev.Dp;
+        s->nsplit = syrk_num_splits(s->dev.Mp, K, ln);
+        TRY(ensure(c, s->syrk_part, (size_t)s->nsplit * K * Mp * Mp * 8));
+        TRY(ensure(c, s->mraw_part, (size_t)maxparts * Mp * KP * 8));
+        TRY(ensure(c, s->esum_part, (size_t)maxparts * Mp * E * 8));
+        CUDA_TRY(c, cudaMemsetAsync(s->syrk_part.p, 0, (size_t)s->nsplit * K * Mp * Mp * 8, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(s->mraw_part.p, 0, (size_t)maxparts * Mp * KP * 8, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(s->esum_part.p, 0, (size_t)maxparts * Mp * E * 8, c->stream));
+        s->mraw_nparts = s->esum_nparts = 0;
+    }
+    const int nblocks_max = mc_num_blocks(ldn);
+    TRY(ensure(c, c->mc_part, (size_t)nblocks_max * MC_NPART * 8));
+
+    for (int64_t c0 = 0; c0 < N_local; c0 += Nc) {
+        const int64_t n = (N_local - c0 < Nc) ? N_local - c0 : Nc;
+        const int64_t ldc = round_up64(n, 64);   // padded extent of THIS chunk (<= ldn); leading dimension stays ldn
+        ChunkBuffers cp = chunk_of(sp, X + c0 * D, n, ldn), ca = chunk_of(sa, X + c0 * D, n, ldn);
+        cond_fwd_a(sp.dev, cp, ln);
+        cond_fwd_b(sp.dev, cp, ln);
+        cond_fwd_a(sa.dev, ca, ln);
+        cond_fwd_b(sa.dev, ca, ln);
+        McArgs m;
+        m.model = cfg->model; m.lik = cfg->lik; m.S = cfg->S; m.K = K;
+        m.temperature = cfg->temperature;
+        m.inv_n_global = 1.0 / (double)cfg->n_global;
+        m.n = n; m.ldn = ldc; m.n_local = N_local; m.chunk_offset = c0;
+        m.Y = Y + c0;
+        m.fmean_p = cp.fmean; m.fvar_p = cp.fvar; m.fmean_a = ca.fmean; m.fvar_a = ca.fvar;
+        m.mubar_p = cp.mubar; m.vbar_p = cp.vbar; m.mubar_a = ca.mubar; m.vbar_a = ca.vbar;
+        m.lik_var = lik_var; m.assign_lik_var = assign_lik_var;
+        m.z = noise->z; m.u = noise->u; m.seed = noise->seed; m.point_offset = noise->point_offset;
+        mc_pass(m, (double*)c->mc_part.p, ln);
+        mc_fold((double*)c->mc_part.p, mc_num_blocks(ldc), reduce_buf, ln);
+        syrk_accumulate(sp.dev, cp, (double*)sp.syrk_part.p, sp.nsplit, ln);
+        syrk_accumulate(sa.dev, ca, (double*)sa.syrk_part.p, sa.nsplit, ln);
+        cond_bwd_a(sp.dev, cp, (double*)sp.mraw_part.p, maxparts, &sp.mraw_nparts, ln);
+        cond_bwd_b(sp.dev, cp, (double*)sp.esum_part.p, maxparts, &sp.esum_nparts, ln);
+        cond_bwd_a(sa.dev, ca, (double*)sa.mraw_part.p, maxparts, &sa.mraw_nparts, ln);
+        cond_bwd_b(sa.dev, ca, (double*)sa.esum_part.p, maxparts, &sa.esum_nparts, ln);
+    }
+    const LayerRB* rbs[2] = {&rp, &ra};
+    for (int i = 0; i < 2; ++i) {
+        LayerSlot* s = slots[i];
+        const int64_t Mp = s->dev.Mp, E = 1 + 2 * s->dev.Dp;
+        reduce_partials(reduce_buf + rbs[i]->S, (const double*)s->syrk_part.p, (int64_t)K * Mp * Mp, s->nsplit,
+                        (int64_t)K * Mp * Mp, false, ln);
+        reduce_partials(reduce_buf + rbs[i]->mraw, (const double*)s->mraw_part.p, Mp * KP, s->mraw_nparts, Mp * KP, false, ln);
+        reduce_partials(reduce_buf + rbs[i]->esum, (const double*)s->esum_part.p, Mp * E, s->esum_nparts, Mp * E, false, ln);
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
+int mgp_elbo_finish(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, const mgp_layer* assign,
+                    const double* lik_var, const double* assign_lik_var, const double* reduce_buf, double* elbo,
+                    mgp_layer_grad* pg, mgp_layer_grad* ag, double* lik_var_grad, double* assign_lik_var_grad) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    TRY(check_cfg(c, cfg, pred, assign, lik_var, assign_lik_var));
+    if (!reduce_buf || !elbo || !pg || !ag) return fail(c, MGP_ERR_BAD_ARG, "elbo_finish: NULL argument");
+    for (const mgp_layer_grad* g : {pg, ag})
+        if (!g->Z || !g->q_mu || !g->q_sqrt || !g->variance || !g->lengthscales)
+            return fail(c, MGP_ERR_BAD_ARG, "elbo_finish: NULL gradient pointer");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const Launch ln = launch_of(c);
+    LayerSlot &sp = c->slot[0], &sa = c->slot[1];
+    TRY(setup_layer(c, sp, pred, true));
+    TRY(setup_layer(c, sa, assign, true));
+    if (!c->pre_valid) {
+        precompute_layer(sp.dev, true, (int*)c->status.p, ln);
+        precompute_layer(sa.dev, true, (int*)c->status.p, ln);
+        c->pre_valid = true;
+    }
+    const int K = pred->K;
+    const LayerRB rp = layer_rb(RB_HEADER, sp.dev.Mp, sp.dev.Dp, K);
+    const LayerRB ra = layer_rb(rp.end, sa.dev.Mp, sa.dev.Dp, K);
+    const double kl_coef = -1.0 / cfg->num_data;
+    double* kl = (double*)c->kl.p;
+    finish_layer(sp.dev, reduce_buf + rp.S, reduce_buf + rp.mraw, reduce_buf + rp.esum, reduce_buf + RB_SUMV_PRED, kl_coef,
+                 pg->Z, pg->q_mu, pg->q_sqrt, pg->variance, pg->lengthscales, kl, ln);
+    finish_layer(sa.dev, reduce_buf + ra.S, reduce_buf + ra.mraw, reduce_buf + ra.esum, reduce_buf + RB_SUMV_ASSIGN, kl_coef,
+                 ag->Z, ag->q_mu, ag->q_sqrt, ag->variance, ag->lengthscales, kl + 1, ln);
+    elbo_finalize_kernel<<<1, 32, 0, c->stream>>>(reduce_buf, kl, cfg->num_data, K, elbo,
+                                                  cfg->lik == MGP_LIK_GAUSSIAN ? lik_var_grad : nullptr,
+                                                  cfg->model == MGP_MODEL_SMGP_MODIFIED ? assign_lik_var_grad : nullptr);
+    c->launches += 1;
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
+int mgp_elbo_fwd_bwd(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, const mgp_layer* assign,
+                     const double* lik_var, const double* assign_lik_var, const double* X, const double* Y,
+                     int64_t N_local, const mgp_noise* noise, double* elbo, mgp_layer_grad* pg, mgp_layer_grad* ag,
+                     double* lik_var_grad, double* assign_lik_var_grad) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    const int64_t len = mgp_reduce_buffer_len(pred, assign);
+    if (len <= 0) return fail(c, MGP_ERR_BAD_ARG, "elbo_fwd_bwd: NULL layer");
+    TRY(check_cfg(c, cfg, pred, assign, lik_var, assign_lik_var));
+    TRY(ensure(c, c->scratch_rb, (size_t)len * 8));
+    TRY(mgp_elbo_local(c, cfg, pred, assign, lik_var, assign_lik_var, X, Y, N_local, noise, (double*)c->scratch_rb.p));
+    return mgp_elbo_finish(c, cfg, pred, assign, lik_var, assign_lik_var, (const double*)c->scratch_rb.p, elbo, pg, ag,
+                           lik_var_grad, assign_lik_var_grad);
+}
+
+int mgp_debug_kuu_chol(mgp_ctx* c, const mgp_layer* layer, double* Kuu, double* L, double* Linv) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    if (!Kuu || !L || !Linv) return fail(c, MGP_ERR_BAD_ARG, "debug_kuu_chol: NULL output");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->pre_valid = false;
+    TRY(setup_layer(c, c->slot[0], layer, false));
+    precompute_layer(c->slot[0].dev, false, (int*)c->status.p, launch_of(c));
+    const LayerDev& d = c->slot[0].dev;
+    const size_t M = d.M, Mp = d.Mp;
+    CUDA_TRY(c, cudaMemcpy2DAsync(Kuu, M * 8, d.Kuu, Mp * 8, M * 8, M, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpy2DAsync(L, M * 8, d.L, Mp * 8, M * 8, M, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpy2DAsync(Linv, M * 8, d.Linv, Mp * 8, M * 8, M, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
+}  // extern "C"

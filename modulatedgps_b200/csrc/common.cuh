@@ -1,0 +1,77 @@
+// Shared device helpers for libmgp (sm_100a).  FP64 tensor-core path = mma.sync m8n8k4 f64, which
+// lowers to DMMA.8x8x4 on sm_100a (tcgen05 has no f64 kind).  Measured issue-rate peak on B200:
+// 37.0 TFLOP/s (profiles/r01_fp64_peak_microbench.txt).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mgp {
+
+// ---- fragment conventions (PTX ISA, mma.m8n8k4 .f64) -------------------------------------------
+//   lane = g*4 + t,  g = lane>>2 (0..7), t = lane&3 (0..3)
+//   A (8x4, row)  : a  = A[g][t]
+//   B (4x8, col)  : b  = B[t][g]           (k = t, n = g)
+//   C/D (8x8)     : c0 = C[g][2t], c1 = C[g][2t+1]
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+// ---- "fragment-major" layout of a left operand W [R x C] (R % 8 == 0, C % 4 == 0) ----------------
+// 8x4 blocks are stored contiguously (32 doubles, element (g,t) at g*4+t), block (rb, kb) at
+// (rb*(C/4) + kb)*32.  A warp reads one A-fragment with a single fully coalesced 256-byte load.
+__host__ __device__ __forceinline__ size_t wf_index(int r, int c, int C) {
+    return ((size_t)(r >> 3) * (size_t)(C >> 2) + (size_t)(c >> 2)) * 32 + (size_t)((r & 7) * 4 + (c & 3));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sum over the 8 "g" groups (lanes with equal t): xor 4, 8, 16
+__device__ __forceinline__ double sum_over_g(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
+
+// sum over the 4 "t" lanes of a group: xor 1, 2
+__device__ __forceinline__ double sum_over_t(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// deterministic block-wide sum of one double per thread; result valid in thread 0.  `red` >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = lane < nw ? red[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int64_t round_up64(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace mgp

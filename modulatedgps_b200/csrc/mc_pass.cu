@@ -1,0 +1,489 @@
+// Fused Monte-Carlo likelihood pass (forward + adjoints) and the small per-point prediction kernels.
+//
+// One thread per point.  Replaces, for S samples at once and without materialising any [S,N,K] temporary:
+//   SMGP.W_dist + reparameterize          MixtureGPs/models.py:55-61, MixtureGPs/utils.py:27
+//   tfp RelaxedOneHotCategorical.sample   models.py:60,73  (gumbel = -log(-log u); exp(log_softmax((g+logits)/T)))
+//   GaussianModified._variational_expectations   MixtureGPs/likelihoods.py:39-41 (per component, not summed)
+//   gpflow MultiClass(RobustMax) expectation via BroadcastingLikelihood   broadcasting_lik.py:26-42
+//   SMGP.E_log_p_Y / SMGPModified.E_log_p_Y      models.py:63-67 / 112-123  (logsumexp over samples)
+// and TF's reverse pass through them.  The pass is HBM-bound: per point it reads 4K conditionals + y and (parity
+// mode) 2 S K noise values, coalesced and vectorised by the [.., N, K] layouts, and writes 4K adjoints.
+// Two sweeps over the samples (online logsumexp, then adjoints) avoid any per-thread [S] storage.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "gh20.h"
+#include "kernels.h"
+
+namespace mgp {
+
+constexpr double REPARAM_JITTER = 1e-6;  // config.default_jitter() in reparameterize, MixtureGPs/utils.py:27
+constexpr int MC_THREADS = 128;
+constexpr double HALF_LOG_2PI = 0.91893853320467274178;
+
+// ---- Philox4x32-10 (throughput mode) --------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+// one standard normal and one uniform on (0,1) for (global point, sample, component, stream)
+__device__ __forceinline__ void philox_draw(uint64_t seed, int64_t point, int s, int k, int stream, double& z,
+                                            double& u) {
+    uint32_t c[4] = {(uint32_t)point, (uint32_t)((uint64_t)point >> 32), (uint32_t)s, (uint32_t)(k | (stream << 8))};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double ua = ((double)c[0] + 0.5) * (1.0 / 4294967296.0);
+    const double ub = ((double)c[1] + 0.5) * (1.0 / 4294967296.0);
+    z = sqrt(-2.0 * log(ua)) * cospi(2.0 * ub);
+    const uint64_t r53 = (((uint64_t)c[2] << 32) | c[3]) >> 11;
+    u = ((double)r53 + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// ---- RobustMax Gauss-Hermite quadrature (gpflow MultiClass) ----------------------------
+__constant__ double c_gh_x[20];
+__constant__ double c_gh_w[20];   // weights / sqrt(pi)
+static bool g_gh_ready = false;
+
+static void ensure_gh(cudaStream_t) {
+    if (g_gh_ready) return;
+    const double* x = GH20_X;
+    const double* w = GH20_W;
+    double ws[20];
+    const double sqrt_pi = 1.7724538509055160273;
+    for (int i = 0; i < 20; ++i) ws[i] = w[i] / sqrt_pi;
+    cudaMemcpyToSymbol(c_gh_x, x, sizeof(double) * 20);
+    cudaMemcpyToSymbol(c_gh_w, ws, sizeof(ws));
+    g_gh_ready = true;
+}
+
+// epsilon after GPflow's Sigmoid-bijector round trip of 1e-3
+__device__ __forceinline__ double robustmax_eps() {
+    const double e = 1e-3;
+    const double x = log(e) - log1p(-e);
+    return 1.0 / (1.0 + exp(-x));
+}
+
+// p = P(f_c is largest) and its gradient w.r.t. mu[.] and var[.]
+template <int K, bool GRAD>
+__device__ __forceinline__ double robustmax_prob(int c, const double (&mu)[K], const double (&var)[K],
+                                                 double (&dmu)[K], double (&dvar)[K]) {
+    const double c1 = 1.0 - 2e-6, INV_SQRT2 = 0.70710678118654752440, INV_SQRT_2PI = 0.39894228040143267794;
+    double sd[K];
+    double mu_c = 0.0, var_c = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        sd[j] = sqrt(fmax(var[j], 1e-10));
+        if (j == c) { mu_c = mu[j]; var_c = var[j]; }
+        if (GRAD) dmu[j] = dvar[j] = 0.0;
+    }
+    const double sdc2 = sqrt(fmax(2.0 * var_c, 1e-10));
+    double p = 0.0, dmu_c = 0.0, dvar_c = 0.0;
+    for (int q = 0; q < 20; ++q) {
+        const double X = mu_c + c_gh_x[q] * sdc2;
+        double cdf[K], dist[K];
+        double prod = 1.0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            dist[j] = (X - mu[j]) / sd[j];
+            cdf[j] = (0.5 * (1.0 + erf(dist[j] * INV_SQRT2))) * c1 + 1e-6;
+            if (j == c) cdf[j] = 1.0;
+            prod *= cdf[j];
+        }
+        p += prod * c_gh_w[q];
+        if (GRAD) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                if (j == c) continue;
+                // d prod / d dist_j
+                const double dd = c_gh_w[q] * (prod / cdf[j]) * c1 * INV_SQRT_2PI * exp(-0.5 * dist[j] * dist[j]);
+                dmu[j] -= dd / sd[j];
+                if (var[j] > 1e-10) dvar[j] -= dd * (X - mu[j]) * 0.5 / (sd[j] * sd[j] * sd[j]);
+                dmu_c += dd / sd[j];
+                if (2.0 * var_c > 1e-10) dvar_c += dd / sd[j] * c_gh_x[q] / sdc2;
+            }
+        }
+    }
+    if (GRAD) {
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+            if (j == c) { dmu[j] = dmu_c; dvar[j] = dvar_c; }
+    }
+    return p;
+}
+
+// relaxed one-hot weights for one sample: W = exp(log_softmax((gumbel + logits)/T))
+template <int K>
+__device__ __forceinline__ void sample_weights(const double (&mu_a)[K], const double (&sd_a)[K], const double (&z)[K],
+                                               const double (&u)[K], double temperature, double (&W)[K]) {
+    double x[K];
+    double mx = -DBL_MAX;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double logit = mu_a[k] + z[k] * sd_a[k];          // reparameterize: mean + z * (var + jitter)**0.5
+        const double gumbel = -log(-log(u[k]));
+        x[k] = (gumbel + logit) / temperature;
+        mx = fmax(mx, x[k]);
+    }
+    double se = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) se += exp(x[k] - mx);
+    const double lse = log(se);
+#pragma unroll
+    for (int k = 0; k < K; ++k) W[k] = exp((x[k] - mx) - lse);
+}
+
+template <int K>
+__device__ __forceinline__ void load_noise(const McArgs& a, int64_t i, int s, double (&z)[K], double (&u)[K]) {
+    if (a.z != nullptr) {
+        const size_t base = ((size_t)s * a.n_local + a.chunk_offset + i) * K;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            z[k] = __ldg(a.z + base + k);
+            u[k] = __ldg(a.u + base + k);
+        }
+    } else {
+        const int64_t point = a.point_offset + a.chunk_offset + i;
+#pragma unroll
+        for (int k = 0; k < K; ++k) philox_draw(a.seed, point, s, k, 0, z[k], u[k]);
+    }
+}
+
+template <int K, int MODEL, int LIK>
+__global__ void __launch_bounds__(MC_THREADS) mc_pass_kernel(McArgs a, double* block_part) {
+    __shared__ double red[32];
+    const int64_t i = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
+    const bool live = i < a.n;
+    double data = 0.0, sumv_p = 0.0, sumv_a = 0.0;
+    double glik[K], galik[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) glik[k] = galik[k] = 0.0;
+
+    if (live) {
+        double mu_p[K], var_p[K], mu_a[K], var_a[K], sd_a[K], e[K], eA[K];
+        const double y = a.Y[i];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            mu_p[k] = a.fmean_p[(size_t)i * K + k];
+            var_p[k] = a.fvar_p[(size_t)i * K + k];
+            mu_a[k] = a.fmean_a[(size_t)i * K + k];
+            var_a[k] = a.fvar_a[(size_t)i * K + k];
+            sd_a[k] = sqrt(var_a[k] + REPARAM_JITTER);
+        }
+        double dp_dmu[K], dp_dvar[K];
+        if (LIK == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double s = a.lik_var[k], r = y - mu_p[k];
+                e[k] = -HALF_LOG_2PI - 0.5 * log(s) - 0.5 * (r * r + var_p[k]) / s;
+            }
+        } else {
+            const double eps = robustmax_eps();
+            const double p = robustmax_prob<K, true>((int)y, mu_p, var_p, dp_dmu, dp_dvar);
+            const double ve = p * log(1.0 - eps) + (1.0 - p) * log(eps / (K - 1.0));
+#pragma unroll
+            for (int k = 0; k < K; ++k) e[k] = ve;
+        }
+        if (MODEL == 1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double s = a.assign_lik_var[k], r = y - mu_a[k];
+                eA[k] = -HALF_LOG_2PI - 0.5 * log(s) - 0.5 * (r * r + var_a[k]) / s;
+            }
+        }
+        // sweep 1: online logsumexp over the samples
+        double my = -DBL_MAX, sy = 0.0, mA = -DBL_MAX, sA = 0.0;
+        for (int s = 0; s < a.S; ++s) {
+            double z[K], u[K], W[K];
+            load_noise<K>(a, i, s, z, u);
+            sample_weights<K>(mu_a, sd_a, z, u, a.temperature, W);
+            double ty = 0.0, tA = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                ty += W[k] * e[k];
+                if (MODEL == 1) tA += W[k] * eA[k];
+            }
+            if (ty > my) { sy = sy * exp(my - ty) + 1.0; my = ty; } else { sy += exp(ty - my); }
+            if (MODEL == 1) {
+                if (tA > mA) { sA = sA * exp(mA - tA) + 1.0; mA = tA; } else { sA += exp(tA - mA); }
+            }
+        }
+        const double logS = log((double)a.S);
+        const double lse_y = log(sy) + my;
+        double lse_A = 0.0;
+        if (MODEL == 1) lse_A = log(sA) + mA;
+        // SMGP: logsumexp_s(t) - log S ; Modified: logsumexp_s(tA - log S) + logsumexp_s(ty - log S)
+        data = (MODEL == 0) ? (lse_y - logS) : ((lse_A - logS) + (lse_y - logS));
+        data *= a.inv_n_global;
+
+        // sweep 2: adjoints
+        double mub_a[K], vb_a[K], ebar[K], eAbar[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) mub_a[k] = vb_a[k] = ebar[k] = eAbar[k] = 0.0;
+        for (int s = 0; s < a.S; ++s) {
+            double z[K], u[K], W[K];
+            load_noise<K>(a, i, s, z, u);
+            sample_weights<K>(mu_a, sd_a, z, u, a.temperature, W);
+            double ty = 0.0, tA = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                ty += W[k] * e[k];
+                if (MODEL == 1) tA += W[k] * eA[k];
+            }
+            const double wy = exp(ty - lse_y) * a.inv_n_global;
+            const double wA = (MODEL == 1) ? exp(tA - lse_A) * a.inv_n_global : 0.0;
+            // d/dW_k, then through exp(log_softmax(x)) :  xbar_k = Wbar_k W_k - W_k sum_j Wbar_j W_j
+            double gW[K], dot = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double wb = wy * e[k];
+                if (MODEL == 1) wb += wA * eA[k];
+                gW[k] = wb * W[k];
+                dot += gW[k];
+                ebar[k] += wy * W[k];
+                if (MODEL == 1) eAbar[k] += wA * W[k];
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double xb = (gW[k] - W[k] * dot) / a.temperature;   // d/d logits_k
+                mub_a[k] += xb;
+                vb_a[k] += xb * z[k] * (0.5 / sd_a[k]);
+            }
+        }
+        // through the likelihood terms
+        double mub_p[K], vb_p[K];
+        if (LIK == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double s = a.lik_var[k], r = y - mu_p[k];
+                mub_p[k] = ebar[k] * r / s;
+                vb_p[k] = -0.5 * ebar[k] / s;
+                glik[k] = ebar[k] * (-0.5 / s + 0.5 * (r * r + var_p[k]) / (s * s));
+            }
+        } else {
+            const double eps = robustmax_eps();
+            double esum = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) esum += ebar[k];
+            const double pbar = esum * (log(1.0 - eps) - log(eps / (K - 1.0)));
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                mub_p[k] = pbar * dp_dmu[k];
+                vb_p[k] = pbar * dp_dvar[k];
+            }
+        }
+        if (MODEL == 1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double s = a.assign_lik_var[k], r = y - mu_a[k];
+                mub_a[k] += eAbar[k] * r / s;
+                vb_a[k] += -0.5 * eAbar[k] / s;
+                galik[k] = eAbar[k] * (-0.5 / s + 0.5 * (r * r + var_a[k]) / (s * s));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            a.mubar_p[(size_t)i * K + k] = mub_p[k];
+            a.vbar_p[(size_t)i * K + k] = vb_p[k];
+            a.mubar_a[(size_t)i * K + k] = mub_a[k];
+            a.vbar_a[(size_t)i * K + k] = vb_a[k];
+            sumv_p += vb_p[k];
+            sumv_a += vb_a[k];
+        }
+    } else if (i < a.ldn) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            a.mubar_p[(size_t)i * K + k] = 0.0;
+            a.vbar_p[(size_t)i * K + k] = 0.0;
+            a.mubar_a[(size_t)i * K + k] = 0.0;
+            a.vbar_a[(size_t)i * K + k] = 0.0;
+        }
+    }
+    // deterministic block partials
+    double* out = block_part + (size_t)blockIdx.x * MC_NPART;
+    double r = block_sum(data, red);
+    if (threadIdx.x == 0) out[0] = r;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        r = block_sum(k < K ? glik[k < K ? k : 0] : 0.0, red);
+        if (threadIdx.x == 0) out[1 + k] = r;
+        r = block_sum(k < K ? galik[k < K ? k : 0] : 0.0, red);
+        if (threadIdx.x == 0) out[9 + k] = r;
+    }
+    r = block_sum(sumv_p, red);
+    if (threadIdx.x == 0) out[17] = r;
+    r = block_sum(sumv_a, red);
+    if (threadIdx.x == 0) out[18] = r;
+    if (threadIdx.x == 0) out[19] = 0.0;
+}
+
+int mc_num_blocks(int64_t ldn) { return (int)((ldn + MC_THREADS - 1) / MC_THREADS); }
+
+template <int K>
+static void mc_dispatch(const McArgs& a, double* block_part, int nblocks, cudaStream_t st) {
+    if (a.model == 0 && a.lik == 0) mc_pass_kernel<K, 0, 0><<<nblocks, MC_THREADS, 0, st>>>(a, block_part);
+    else if (a.model == 0 && a.lik == 1) mc_pass_kernel<K, 0, 1><<<nblocks, MC_THREADS, 0, st>>>(a, block_part);
+    else if (a.model == 1 && a.lik == 0) mc_pass_kernel<K, 1, 0><<<nblocks, MC_THREADS, 0, st>>>(a, block_part);
+    else mc_pass_kernel<K, 1, 1><<<nblocks, MC_THREADS, 0, st>>>(a, block_part);
+}
+
+void mc_pass(const McArgs& a, double* block_part, const Launch& ln) {
+    ensure_gh(ln.stream);
+    const int nblocks = mc_num_blocks(a.ldn);
+    switch (a.K) {
+        case 1: mc_dispatch<1>(a, block_part, nblocks, ln.stream); break;
+        case 2: mc_dispatch<2>(a, block_part, nblocks, ln.stream); break;
+        case 3: mc_dispatch<3>(a, block_part, nblocks, ln.stream); break;
+        case 4: mc_dispatch<4>(a, block_part, nblocks, ln.stream); break;
+        case 5: mc_dispatch<5>(a, block_part, nblocks, ln.stream); break;
+        case 6: mc_dispatch<6>(a, block_part, nblocks, ln.stream); break;
+        case 7: mc_dispatch<7>(a, block_part, nblocks, ln.stream); break;
+        default: mc_dispatch<8>(a, block_part, nblocks, ln.stream); break;
+    }
+    ln.tick();
+}
+
+// header[0..19) += sum over blocks (single block, fixed order)
+__global__ void __launch_bounds__(256) mc_fold_kernel(const double* block_part, int nblocks, double* hdr) {
+    __shared__ double red[32];
+    for (int q = 0; q < MC_NPART - 1; ++q) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += block_part[(size_t)b * MC_NPART + q];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) hdr[q] += s;
+        __syncthreads();
+    }
+}
+
+void mc_fold(const double* block_part, int nblocks, double* rb_header, const Launch& ln) {
+    mc_fold_kernel<<<1, 256, 0, ln.stream>>>(block_part, nblocks, rb_header);
+    ln.tick();
+}
+
+// ==================================================================================================
+// prediction kernels
+// ==================================================================================================
+// SMGP.predict_assign: softmax_K(mean_S(mu)) — the S tiled copies are identical, so the mean is mu itself
+__global__ void predict_assign_k(const double* fmean, int64_t n, int K, double* probs, int64_t* argmax) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double mx = -DBL_MAX;
+    for (int k = 0; k < K; ++k) mx = fmax(mx, fmean[(size_t)i * K + k]);
+    double se = 0.0;
+    for (int k = 0; k < K; ++k) se += exp(fmean[(size_t)i * K + k] - mx);
+    double best = -1.0;
+    int64_t arg = 0;
+    for (int k = 0; k < K; ++k) {
+        const double p = exp(fmean[(size_t)i * K + k] - mx) / se;
+        probs[(size_t)i * K + k] = p;
+        if (p > best) { best = p; arg = k; }   // first maximum wins, as np.argmax / tf.argmax
+    }
+    argmax[i] = arg;
+}
+
+void predict_assign_kernel(const double* fmean, int64_t n, int K, double* probs, int64_t* argmax, const Launch& ln) {
+    if (n <= 0) return;
+    predict_assign_k<<<(unsigned)((n + 127) / 128), 128, 0, ln.stream>>>(fmean, n, K, probs, argmax);
+    ln.tick();
+}
+
+template <int K>
+__global__ void predict_y_k(const double* fmean, const double* fvar, int64_t n, int lik, const double* lik_var,
+                            double* mean, double* var) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double mu[K], v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { mu[k] = fmean[(size_t)i * K + k]; v[k] = fvar[(size_t)i * K + k]; }
+    if (lik == 0) {   // GaussianModified._predict_mean_and_var: (Fmu, Fvar + variance)
+#pragma unroll
+        for (int k = 0; k < K; ++k) { mean[(size_t)i * K + k] = mu[k]; var[(size_t)i * K + k] = v[k] + lik_var[k]; }
+    } else {          // MultiClass._predict_mean_and_var
+        const double eps = robustmax_eps();
+        double d0[K], d1[K];
+        for (int c = 0; c < K; ++c) {
+            const double p = robustmax_prob<K, false>(c, mu, v, d0, d1);
+            const double ps = p * (1.0 - eps) + (1.0 - p) * (eps / (K - 1.0));
+            mean[(size_t)i * K + c] = ps;
+            var[(size_t)i * K + c] = ps - ps * ps;
+        }
+    }
+}
+
+void predict_y_kernel(const double* fmean, const double* fvar, int64_t n, int K, int lik, const double* lik_var,
+                      double* mean, double* var, const Launch& ln) {
+    if (n <= 0) return;
+    ensure_gh(ln.stream);
+    const unsigned grid = (unsigned)((n + 127) / 128);
+#define PY(KK) case KK: predict_y_k<KK><<<grid, 128, 0, ln.stream>>>(fmean, fvar, n, lik, lik_var, mean, var); break;
+    switch (K) { PY(1) PY(2) PY(3) PY(4) PY(5) PY(6) PY(7) default: predict_y_k<8><<<grid, 128, 0, ln.stream>>>(fmean, fvar, n, lik, lik_var, mean, var); }
+#undef PY
+    ln.tick();
+}
+
+// SMGP.predict_samples (models.py:91-103): one thread per (sample, point)
+template <int K>
+__global__ void predict_samples_k(SampleArgs a) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)a.S * a.n) return;
+    const int s = (int)(idx / a.n);
+    const int64_t i = idx % a.n;
+    double mu_a[K], sd_a[K], z[K], u[K], zp[K], W[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        mu_a[k] = a.fmean_a[(size_t)i * K + k];
+        sd_a[k] = sqrt(a.fvar_a[(size_t)i * K + k] + REPARAM_JITTER);
+        if (a.z != nullptr) {
+            z[k] = a.z[((size_t)s * a.n + i) * K + k];
+            u[k] = a.u[((size_t)s * a.n + i) * K + k];
+            zp[k] = a.z_pred[((size_t)s * a.n + i) * K + k];
+        } else {
+            double dummy;
+            philox_draw(a.seed, a.point_offset + i, s, k, 0, z[k], u[k]);
+            philox_draw(a.seed, a.point_offset + i, s, k, 1, zp[k], dummy);
+        }
+    }
+    sample_weights<K>(mu_a, sd_a, z, u, a.temperature, W);
+    double mu[K], v[K], my[K], vy[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { mu[k] = a.fmean_p[(size_t)i * K + k]; v[k] = a.fvar_p[(size_t)i * K + k]; }
+    if (a.lik == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) { my[k] = mu[k]; vy[k] = v[k] + a.lik_var[k]; }
+    } else {
+        const double eps = robustmax_eps();
+        double d0[K], d1[K];
+        for (int c = 0; c < K; ++c) {
+            const double p = robustmax_prob<K, false>(c, mu, v, d0, d1);
+            my[c] = p * (1.0 - eps) + (1.0 - p) * (eps / (K - 1.0));
+            vy[c] = my[c] - my[c] * my[c];
+        }
+    }
+    double sy = 0.0, sf = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        sy += (my[k] + zp[k] * sqrt(vy[k] + REPARAM_JITTER)) * W[k];   // reparameterize(mean, var, z) * W
+        sf += (mu[k] + zp[k] * sqrt(v[k] + REPARAM_JITTER)) * W[k];
+    }
+    a.samples_y[idx] = sy;
+    a.samples_f[idx] = sf;
+}
+
+void predict_samples_kernel(const SampleArgs& a, const Launch& ln) {
+    const int64_t total = (int64_t)a.S * a.n;
+    if (total <= 0) return;
+    ensure_gh(ln.stream);
+    const unsigned grid = (unsigned)((total + 127) / 128);
+#define PS(KK) case KK: predict_samples_k<KK><<<grid, 128, 0, ln.stream>>>(a); break;
+    switch (a.K) { PS(1) PS(2) PS(3) PS(4) PS(5) PS(6) PS(7) default: predict_samples_k<8><<<grid, 128, 0, ln.stream>>>(a); }
+#undef PS
+    ln.tick();
+}
+
+}  // namespace mgp

@@ -1,0 +1,501 @@
+// Replicated (per-rank) small-matrix work of one SVGP layer: Kuu, Cholesky, L^-1, operand packing,
+// and the backward of all of it (Cholesky backward, kernel backward on Kuu, KL terms).
+//
+// Reference arithmetic being replaced:
+//   Kuu            gpflow covariances.Kuu + SquaredExponential.K      (call site MixtureGPs/models.py:135)
+//   chol / solve   gpflow base_conditional: cholesky, triangular_solve (call site models.py:141-143)
+//   KL             gpflow gauss_kl, whitened                           (call site models.py:79)
+//   backward       TF autodiff of the above                            (utils/training_utils.py:8-10)
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mgp {
+
+constexpr double JITTER = 1e-6;  // gpflow.config.default_jitter(), MixtureGPs/models.py:17,135
+
+// --------------------------------------------------------------------------------------------------
+// Zs = Z / lengthscales (row-major and fragment-major), |Zs_i|^2, 1/lengthscale
+// --------------------------------------------------------------------------------------------------
+__global__ void prep_z_kernel(LayerDev ly) {
+    const int Mp = ly.Mp, Dp = ly.Dp, M = ly.M, D = ly.D;
+    for (int d = threadIdx.x; d < Dp; d += blockDim.x)
+        ly.inv_ls[d] = d < D ? 1.0 / ly.lengthscales[ly.n_ls == 1 ? 0 : d] : 0.0;
+    for (int idx = threadIdx.x; idx < Mp * Dp; idx += blockDim.x) {
+        const int i = idx / Dp, d = idx % Dp;
+        double v = 0.0;
+        if (i < M && d < D) v = ly.Z[(size_t)i * D + d] / ly.lengthscales[ly.n_ls == 1 ? 0 : d];  // Stationary.scale
+        ly.Zs_rm[idx] = v;
+        ly.Zs_fm[wf_index(i, d, Dp)] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Mp; i += blockDim.x) {
+        double s = 0.0;
+        for (int d = 0; d < Dp; ++d) {
+            const double v = ly.Zs_rm[(size_t)i * Dp + d];
+            s += v * v;
+        }
+        ly.zs2[i] = s;
+    }
+}
+
+// Kuu = variance * exp(-r2/2) + jitter I, r2 = -2 Zs Zs^T + (|zs_i|^2 + |zs_j|^2)   (square_distance, X2=None)
+__global__ void kuu_kernel(LayerDev ly) {
+    const int Mp = ly.Mp, Dp = ly.Dp, M = ly.M;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Mp * Mp) return;
+    const int i = idx / Mp, j = idx % Mp;
+    double v;
+    if (i < M && j < M) {
+        double dot = 0.0;
+        for (int d = 0; d < Dp; ++d) dot += ly.Zs_rm[(size_t)i * Dp + d] * ly.Zs_rm[(size_t)j * Dp + d];
+        const double r2 = -2.0 * dot + (ly.zs2[i] + ly.zs2[j]);
+        v = ly.variance[0] * exp(-0.5 * r2);
+        if (i == j) v += JITTER;
+    } else {
+        v = (i == j) ? 1.0 : 0.0;  // padding: decoupled unit block
+    }
+    ly.Kuu[idx] = v;
+}
+
+// --------------------------------------------------------------------------------------------------
+// Blocked right-looking Cholesky, one CTA per matrix (matrix stays in L2; 32-wide panels).
+//   (1) diagonal 32x32 block: one warp, one row per lane in registers, warp shuffles for the pivots
+//   (2) panel solve: one row per thread against the diagonal block held in shared memory
+//   (3) trailing update on DMMA, one 32x32 tile per warp
+// --------------------------------------------------------------------------------------------------
+constexpr int CHOL_THREADS = 512;
+
+__global__ void __launch_bounds__(CHOL_THREADS, 1) chol_kernel(double* L, int Mp, int* status) {
+    __shared__ double Dg[32][33];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int nblk = Mp / 32;
+    for (int jb = 0; jb < nblk; ++jb) {
+        const int j0 = jb * 32;
+        if (warp == 0) {
+            double row[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) row[c] = L[(size_t)(j0 + lane) * Mp + j0 + c];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const double piv = __shfl_sync(0xffffffffu, row[c], c);
+                if (!(piv > 0.0) && lane == 0) atomicOr(status, 1);
+                const double d = sqrt(piv);
+                const double l = (lane == c) ? d : row[c] / d;
+                row[c] = l;
+#pragma unroll
+                for (int cc = c + 1; cc < 32; ++cc) {
+                    const double lcc = __shfl_sync(0xffffffffu, l, cc);
+                    row[cc] -= l * lcc;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const double v = (c <= lane) ? row[c] : 0.0;
+                Dg[lane][c] = v;
+                L[(size_t)(j0 + lane) * Mp + j0 + c] = v;
+            }
+        }
+        __syncthreads();
+        // volatile view: keeps the compiler from hoisting all 528 diagonal-block loads out of the row loop
+        const volatile double(*Dv)[33] = Dg;
+        for (int i = j0 + 32 + tid; i < Mp; i += CHOL_THREADS) {
+            double x[32];
+            double* rowp = L + (size_t)i * Mp + j0;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) x[c] = rowp[c];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                double s = x[c];
+#pragma unroll
+                for (int p = 0; p < c; ++p) s -= x[p] * Dv[c][p];
+                x[c] = s / Dv[c][c];
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) rowp[c] = x[c];
+        }
+        __syncthreads();
+        const int nb = nblk - jb - 1;
+        const int ntile = nb * (nb + 1) / 2;
+        for (int tile = warp; tile < ntile; tile += CHOL_THREADS / 32) {
+            int ti = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
+            while (ti * (ti + 1) / 2 > tile) --ti;
+            while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+            const int tj = tile - ti * (ti + 1) / 2;
+            const int r0 = j0 + 32 + ti * 32, c0 = j0 + 32 + tj * 32;
+            double acc[4][4][2];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+#pragma unroll 2
+            for (int kk = 0; kk < 8; ++kk) {
+                double a[4], b[4];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) a[mi] = L[(size_t)(r0 + mi * 8 + g) * Mp + j0 + kk * 4 + t];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) b[ni] = L[(size_t)(c0 + ni * 8 + g) * Mp + j0 + kk * 4 + t];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni], a[mi], b[ni]);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) {
+                    double* p = L + (size_t)(r0 + mi * 8 + g) * Mp + c0 + ni * 8 + 2 * t;
+                    p[0] -= acc[mi][ni][0];
+                    p[1] -= acc[mi][ni][1];
+                }
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < Mp * Mp; idx += CHOL_THREADS) {
+        const int i = idx / Mp, j = idx % Mp;
+        if (j > i) L[idx] = 0.0;
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// X = L^-1 by block forward substitution, one CTA per 32-column block of X (X pre-zeroed).
+// --------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) trinv_kernel(const double* L, double* X, int Mp) {
+    __shared__ double Dii[32][33];
+    __shared__ double R[32][33];
+    const int jb = blockIdx.x, nblk = Mp / 32, tid = threadIdx.x;
+    const int r = tid >> 3, c4 = (tid & 7) * 4;
+    for (int ib = jb; ib < nblk; ++ib) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* Lrow = L + (size_t)(ib * 32 + r) * Mp;
+        for (int p = jb * 32; p < ib * 32; ++p) {
+            const double l = Lrow[p];
+            const double* xr = X + (size_t)p * Mp + jb * 32 + c4;
+            acc[0] += l * xr[0];
+            acc[1] += l * xr[1];
+            acc[2] += l * xr[2];
+            acc[3] += l * xr[3];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) R[r][c4 + q] = ((ib == jb && r == c4 + q) ? 1.0 : 0.0) - acc[q];
+        for (int idx = tid; idx < 1024; idx += 256)
+            Dii[idx >> 5][idx & 31] = L[(size_t)(ib * 32 + (idx >> 5)) * Mp + ib * 32 + (idx & 31)];
+        __syncthreads();
+        if (tid < 32) {
+            double y[32];
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+                double s = R[rr][tid];
+#pragma unroll
+                for (int q = 0; q < rr; ++q) s -= Dii[rr][q] * y[q];
+                y[rr] = s / Dii[rr][rr];
+            }
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) R[rr][tid] = y[rr];
+        }
+        __syncthreads();
+        for (int idx = tid; idx < 1024; idx += 256)
+            X[(size_t)(ib * 32 + (idx >> 5)) * Mp + jb * 32 + (idx & 31)] = R[idx >> 5][idx & 31];
+        __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// packing into fragment-major operands
+// --------------------------------------------------------------------------------------------------
+// W[r][c_off + c] = (transpose ? src[c*ld + r] : src[r*ld + c]) inside the valid source range, else 0
+__global__ void pack_fm_kernel(double* dst, int Rp, int Cp, int c_off, int Ctot, const double* src, int ld,
+                               int Rvalid, int Cvalid, int transpose, int64_t dst_bstride, int64_t src_bstride) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)Rp * Cp) return;
+    const int r = (int)(idx / Cp), c = (int)(idx % Cp);
+    const double* s = src + (int64_t)blockIdx.y * src_bstride;
+    double* d = dst + (int64_t)blockIdx.y * dst_bstride;
+    double v = 0.0;
+    if (r < Rvalid && c < Cvalid) v = transpose ? s[(size_t)c * ld + r] : s[(size_t)r * ld + c];
+    d[wf_index(r, c_off + c, Ctot)] = v;
+}
+
+static void pack_fm(double* dst, int Rp, int Cp, int c_off, int Ctot, const double* src, int ld, int Rvalid,
+                    int Cvalid, bool transpose, int batch, int64_t dst_bstride, int64_t src_bstride,
+                    const Launch& ln) {
+    const int64_t n = (int64_t)Rp * Cp;
+    dim3 grid((unsigned)((n + 255) / 256), batch);
+    pack_fm_kernel<<<grid, 256, 0, ln.stream>>>(dst, Rp, Cp, c_off, Ctot, src, ld, Rvalid, Cvalid, transpose ? 1 : 0,
+                                                dst_bstride, src_bstride);
+    ln.tick();
+}
+
+// Lq_rm[k] = tril(q_sqrt[k]) zero padded to Mp x Mp   (band_part(q_sqrt, -1, 0))
+__global__ void lq_clean_kernel(LayerDev ly) {
+    const int Mp = ly.Mp, M = ly.M;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)ly.K * Mp * Mp) return;
+    const int k = (int)(idx / ((int64_t)Mp * Mp));
+    const int rem = (int)(idx % ((int64_t)Mp * Mp));
+    const int i = rem / Mp, j = rem % Mp;
+    ly.Lq_rm[idx] = (i < M && j <= i) ? ly.q_sqrt[((size_t)k * M + i) * M + j] : 0.0;
+}
+
+// Q_rm[k] = 2 (T1[k] - I_M)
+__global__ void q_finish_kernel(LayerDev ly) {
+    const int Mp = ly.Mp, M = ly.M;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)ly.K * Mp * Mp) return;
+    const int rem = (int)(idx % ((int64_t)Mp * Mp));
+    const int i = rem / Mp, j = rem % Mp;
+    ly.Q_rm[idx] = 2.0 * (ly.T1[idx] - ((i == j && i < M) ? 1.0 : 0.0));
+}
+
+void precompute_layer(const LayerDev& ly, bool need_bwd, int* d_status, const Launch& ln) {
+    const int Mp = ly.Mp, K = ly.K;
+    const int64_t mm = (int64_t)Mp * Mp;
+    prep_z_kernel<<<1, 1024, 0, ln.stream>>>(ly);
+    kuu_kernel<<<(unsigned)((mm + 255) / 256), 256, 0, ln.stream>>>(ly);
+    ln.tick(2);
+    cudaMemcpyAsync(ly.L, ly.Kuu, sizeof(double) * mm, cudaMemcpyDeviceToDevice, ln.stream);
+    chol_kernel<<<1, CHOL_THREADS, 0, ln.stream>>>(ly.L, Mp, d_status);
+    cudaMemsetAsync(ly.Linv, 0, sizeof(double) * mm, ln.stream);
+    trinv_kernel<<<Mp / 32, 256, 0, ln.stream>>>(ly.L, ly.Linv, Mp);
+    ln.tick(2);
+    pack_fm(ly.W_Linv, Mp, Mp, 0, Mp, ly.Linv, Mp, Mp, Mp, false, 1, 0, 0, ln);
+    pack_fm(ly.W_LinvT, Mp, Mp, 0, Mp, ly.Linv, Mp, Mp, Mp, true, 1, 0, 0, ln);
+    lq_clean_kernel<<<(unsigned)((K * mm + 255) / 256), 256, 0, ln.stream>>>(ly);
+    ln.tick();
+    pack_fm(ly.W_LqT, Mp, Mp, 0, Mp, ly.Lq_rm, Mp, Mp, Mp, true, K, mm, mm, ln);
+    pack_fm(ly.W_mT, 16, Mp, 0, Mp, ly.q_mu, K, K, ly.M, true, 1, 0, 0, ln);
+    if (need_bwd) {
+        gemm_small(Mp, Mp, Mp, 1.0, ly.Lq_rm, Mp, mm, false, ly.Lq_rm, Mp, mm, true, 0.0, ly.T1, Mp, mm, K, ln);
+        q_finish_kernel<<<(unsigned)((K * mm + 255) / 256), 256, 0, ln.stream>>>(ly);
+        ln.tick();
+        const int Ctot = K * Mp + KP;
+        for (int k = 0; k < K; ++k)
+            pack_fm(ly.W_Q, Mp, Mp, k * Mp, Ctot, ly.Q_rm + (int64_t)k * mm, Mp, Mp, Mp, false, 1, 0, 0, ln);
+        pack_fm(ly.W_Q, Mp, KP, K * Mp, Ctot, ly.q_mu, K, ly.M, K, false, 1, 0, 0, ln);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------
+// deterministic reduction of per-CTA partial sums
+// --------------------------------------------------------------------------------------------------
+__global__ void reduce_partials_kernel(double* dst, const double* src, int64_t n, int nparts, int64_t stride,
+                                       int accumulate) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = accumulate ? dst[i] : 0.0;
+    for (int p = 0; p < nparts; ++p) s += src[(int64_t)p * stride + i];
+    dst[i] = s;
+}
+
+void reduce_partials(double* dst, const double* src, int64_t n, int nparts, int64_t stride, bool accumulate,
+                     const Launch& ln) {
+    if (n <= 0) return;
+    reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ln.stream>>>(dst, src, n, nparts, stride,
+                                                                               accumulate ? 1 : 0);
+    ln.tick();
+}
+
+// --------------------------------------------------------------------------------------------------
+// replicated backward
+// --------------------------------------------------------------------------------------------------
+// Sfull[k][i][j] = S[k][max(i,j)][min(i,j)]
+__global__ void symmetrize_kernel(double* Sfull, const double* S, int Mp, int K) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)K * Mp * Mp) return;
+    const int64_t mm = (int64_t)Mp * Mp;
+    const int k = (int)(idx / mm);
+    const int rem = (int)(idx % mm);
+    const int i = rem / Mp, j = rem % Mp;
+    Sfull[idx] = (j <= i) ? S[idx] : S[(int64_t)k * mm + (size_t)j * Mp + i];
+}
+
+// dELBO/dq_sqrt[k] = tril(2 S_k Lq_k) + c (Lq_k - diag(1/diag Lq_k)),   c = -1/num_data   (T1 = S_k Lq_k)
+__global__ void gqsqrt_kernel(LayerDev ly, double kl_coef, double* gqsqrt) {
+    const int M = ly.M, Mp = ly.Mp;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)ly.K * M * M) return;
+    const int k = (int)(idx / ((int64_t)M * M));
+    const int rem = (int)(idx % ((int64_t)M * M));
+    const int i = rem / M, j = rem % M;
+    double v = 0.0;
+    if (j <= i) {
+        const size_t p = ((size_t)k * Mp + i) * Mp + j;
+        const double lq = ly.Lq_rm[p];
+        v = 2.0 * ly.T1[p] + kl_coef * (lq - (i == j ? 1.0 / lq : 0.0));
+    }
+    gqsqrt[idx] = v;
+}
+
+__global__ void gqmu_kernel(LayerDev ly, const double* mraw, double kl_coef, double* gqmu) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ly.M * ly.K) return;
+    const int i = idx / ly.K, k = idx % ly.K;
+    gqmu[idx] = mraw[(size_t)i * KP + k] + kl_coef * ly.q_mu[idx];
+}
+
+// T2 = tril(T2 + q_mu mraw^T)
+__global__ void t_finish_kernel(LayerDev ly, const double* mraw) {
+    const int Mp = ly.Mp, M = ly.M, K = ly.K;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Mp * Mp) return;
+    const int i = idx / Mp, j = idx % Mp;
+    double v = 0.0;
+    if (j <= i) {
+        v = ly.T2[idx];
+        if (i < M && j < M)
+            for (int k = 0; k < K; ++k) v += ly.q_mu[(size_t)i * K + k] * mraw[(size_t)j * KP + k];
+    }
+    ly.T2[idx] = v;
+}
+
+// in place: X = -tril(X)
+__global__ void neg_tril_kernel(double* X, int Mp) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Mp * Mp) return;
+    const int i = idx / Mp, j = idx % Mp;
+    X[idx] = (j <= i) ? -X[idx] : 0.0;
+}
+
+// dst = Phi(src) + Phi(src)^T, Phi = lower triangle with halved diagonal
+__global__ void phi_sym_kernel(double* dst, const double* src, int Mp) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Mp * Mp) return;
+    const int i = idx / Mp, j = idx % Mp;
+    dst[idx] = (i >= j) ? src[(size_t)i * Mp + j] : src[(size_t)j * Mp + i];
+}
+
+// kernel backward on Kuu: one CTA per inducing row a.  Kbar2 = Linv^T (P + P^T) Linv = 2 * Kuu_bar.
+// rowout[a] = [ dZs_a[0..Dp) | dls_a[0..Dp) | dvar_a ]   (scaled coordinates)
+__global__ void __launch_bounds__(128) kuu_bwd_kernel(LayerDev ly, const double* Kbar2, double* rowout) {
+    __shared__ double red[32];
+    const int a = blockIdx.x, M = ly.M, Mp = ly.Mp, Dp = ly.Dp, D = ly.D;
+    const double var = ly.variance[0];
+    const int W = 2 * Dp + 1;
+    for (int q = 0; q < W; ++q) {
+        double s = 0.0;
+        for (int j = threadIdx.x; j < M; j += blockDim.x) {
+            double kc = ly.Kuu[(size_t)a * Mp + j];
+            if (j == a) kc -= JITTER;
+            const double gk = 0.5 * Kbar2[(size_t)a * Mp + j] * kc;  // Kuu_bar_aj * K_aj
+            if (q < Dp) {
+                if (q < D) {
+                    const double dz = ly.Zs_rm[(size_t)a * Dp + q] - ly.Zs_rm[(size_t)j * Dp + q];
+                    s += -2.0 * gk * dz;  // both arguments of k(Z,Z); Kuu_bar symmetric
+                }
+            } else if (q < 2 * Dp) {
+                const int d = q - Dp;
+                if (d < D) {
+                    const double dz = ly.Zs_rm[(size_t)a * Dp + d] - ly.Zs_rm[(size_t)j * Dp + d];
+                    s += gk * dz * dz;
+                }
+            } else {
+                s += gk / var;
+            }
+        }
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) rowout[(size_t)a * W + q] = s;
+        __syncthreads();
+    }
+}
+
+// gauss_kl (whitened): 0.5 [ sum q_mu^2 - M K - sum log diag(Lq)^2 + sum Lq^2 ]
+__global__ void __launch_bounds__(256) kl_kernel(LayerDev ly, double* kl_out) {
+    __shared__ double red[32];
+    const int M = ly.M, Mp = ly.Mp, K = ly.K;
+    double s = 0.0;
+    for (int idx = threadIdx.x; idx < M * K; idx += blockDim.x) {
+        const double v = ly.q_mu[idx];
+        s += v * v;
+    }
+    for (int64_t idx = threadIdx.x; idx < (int64_t)K * M * M; idx += blockDim.x) {
+        const int k = (int)(idx / ((int64_t)M * M));
+        const int rem = (int)(idx % ((int64_t)M * M));
+        const int i = rem / M, j = rem % M;
+        if (j <= i) {
+            const double v = ly.Lq_rm[((size_t)k * Mp + i) * Mp + j];
+            s += v * v;
+            if (i == j) s -= log(v * v);
+        }
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) kl_out[0] = 0.5 * (s - (double)M * (double)K);
+}
+
+// final assembly of dZ, dlengthscales, dvariance from the streamed sums (esum), the Kuu path (rowout) and Knn
+__global__ void __launch_bounds__(256) assemble_kernel(LayerDev ly, const double* esum, const double* rowout,
+                                                       const double* sumv, double* gZ, double* gvar, double* gls) {
+    __shared__ double red[32];
+    const int M = ly.M, D = ly.D, Dp = ly.Dp;
+    const int E = 1 + 2 * Dp, W = 2 * Dp + 1;
+    for (int idx = threadIdx.x; idx < M * D; idx += blockDim.x) {
+        const int a = idx / D, d = idx % D;
+        const double zs = ly.Zs_rm[(size_t)a * Dp + d];
+        const double dzs = (esum[(size_t)a * E + 1 + d] - zs * esum[(size_t)a * E]) + rowout[(size_t)a * W + d];
+        gZ[idx] = dzs * ly.inv_ls[d];
+    }
+    double total_ls = 0.0;
+    for (int d = 0; d < D; ++d) {
+        double s = 0.0;
+        for (int a = threadIdx.x; a < M; a += blockDim.x) {
+            const double zs = ly.Zs_rm[(size_t)a * Dp + d];
+            s += esum[(size_t)a * E + 1 + Dp + d] - 2.0 * zs * esum[(size_t)a * E + 1 + d] +
+                 zs * zs * esum[(size_t)a * E] + rowout[(size_t)a * W + Dp + d];
+        }
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) {
+            const double g = s * ly.inv_ls[d];
+            if (ly.n_ls == 1) total_ls += g; else gls[d] = g;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && ly.n_ls == 1) gls[0] = total_ls;
+    double s = 0.0;
+    for (int a = threadIdx.x; a < M; a += blockDim.x) s += esum[(size_t)a * E] / ly.variance[0] + rowout[(size_t)a * W + 2 * Dp];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) gvar[0] = s + sumv[0];
+}
+
+void prior_kl_layer(const LayerDev& ly, double* kl_out, const Launch& ln) {
+    const int64_t mm = (int64_t)ly.Mp * ly.Mp;
+    lq_clean_kernel<<<(unsigned)((ly.K * mm + 255) / 256), 256, 0, ln.stream>>>(ly);
+    kl_kernel<<<1, 256, 0, ln.stream>>>(ly, kl_out);
+    ln.tick(2);
+}
+
+void finish_layer(const LayerDev& ly, const double* S_lower, const double* mraw, const double* esum,
+                  const double* sumv, double kl_coef, double* gZ, double* gqmu, double* gqsqrt, double* gvar,
+                  double* gls, double* kl_out, const Launch& ln) {
+    const int Mp = ly.Mp, K = ly.K, M = ly.M;
+    const int64_t mm = (int64_t)Mp * Mp;
+    const unsigned gmm = (unsigned)((mm + 255) / 256);
+    symmetrize_kernel<<<(unsigned)((K * mm + 255) / 256), 256, 0, ln.stream>>>(ly.Sfull, S_lower, Mp, K);
+    ln.tick();
+    // dq_sqrt
+    gemm_small(Mp, Mp, Mp, 1.0, ly.Sfull, Mp, mm, false, ly.Lq_rm, Mp, mm, false, 0.0, ly.T1, Mp, mm, K, ln);
+    gqsqrt_kernel<<<(unsigned)(((int64_t)K * M * M + 255) / 256), 256, 0, ln.stream>>>(ly, kl_coef, gqsqrt);
+    gqmu_kernel<<<(M * K + 255) / 256, 256, 0, ln.stream>>>(ly, mraw, kl_coef, gqmu);
+    ln.tick(2);
+    // T = tril( sum_k Q_k S_k + q_mu mraw^T )  ( = Abar A^T )
+    for (int k = 0; k < K; ++k)
+        gemm_small(Mp, Mp, Mp, 1.0, ly.Q_rm + k * mm, Mp, 0, false, ly.Sfull + k * mm, Mp, 0, false, k ? 1.0 : 0.0,
+                   ly.T2, Mp, 0, 1, ln);
+    t_finish_kernel<<<gmm, 256, 0, ln.stream>>>(ly, mraw);
+    // Lbar = -tril(L^-T T)
+    gemm_small(Mp, Mp, Mp, 1.0, ly.Linv, Mp, 0, true, ly.T2, Mp, 0, false, 0.0, ly.T3, Mp, 0, 1, ln);
+    neg_tril_kernel<<<gmm, 256, 0, ln.stream>>>(ly.T3, Mp);
+    // Cholesky backward (Murray 2016): Kbar = 1/2 L^-T (P + P^T) L^-1, P = Phi(L^T Lbar)
+    gemm_small(Mp, Mp, Mp, 1.0, ly.L, Mp, 0, true, ly.T3, Mp, 0, false, 0.0, ly.T2, Mp, 0, 1, ln);
+    phi_sym_kernel<<<gmm, 256, 0, ln.stream>>>(ly.T3, ly.T2, Mp);
+    gemm_small(Mp, Mp, Mp, 1.0, ly.Linv, Mp, 0, true, ly.T3, Mp, 0, false, 0.0, ly.T2, Mp, 0, 1, ln);
+    gemm_small(Mp, Mp, Mp, 1.0, ly.T2, Mp, 0, false, ly.Linv, Mp, 0, false, 0.0, ly.T3, Mp, 0, 1, ln);
+    ln.tick(3);
+    // kernel backward on Kuu
+    kuu_bwd_kernel<<<M, 128, 0, ln.stream>>>(ly, ly.T3, ly.rowout);
+    assemble_kernel<<<1, 256, 0, ln.stream>>>(ly, esum, ly.rowout, sumv, gZ, gvar, gls);
+    kl_kernel<<<1, 256, 0, ln.stream>>>(ly, kl_out);
+    ln.tick(3);
+}
+
+}  // namespace mgp

@@ -1,0 +1,527 @@
+// The N-streaming FP64 tensor-core kernels of the SVGP conditional, forward and backward.
+//
+// Every kernel has the same shape: a persistent CTA walks over tiles of NT points; per tile it stages one
+// [Mp x NT] right operand T in shared memory (generated RBF cross-covariances, or a slab of a materialised
+// [Mp, N] array), and each warp computes 16-row blocks  C = W[rows, k-range] * T  on DMMA.8x8x4 with the
+// left operand W streamed from L2 in fragment-major order (one coalesced 256-byte load per fragment).
+// Triangular left operands only visit their non-zero k-range; 16-row blocks are dealt to the 8 warps in
+// snake order so that the triangular work is balanced.
+//
+//   cond_fwd_a : T = Kuf tile (r^2 contraction on DMMA + exp)   A = L^-1 T            -> A, |a_n|^2
+//   cond_fwd_b : T = A tile        B_k = Lq_k^T T (norms only), mean = q_mu^T T       -> fmean, fvar
+//   cond_bwd_a : T = A tile        Abar = sum_k Q_k T diag(vbar_k) + q_mu mubar^T     -> Abar (over A), A mubar
+//   cond_bwd_b : T = Abar tile     Kuf_bar = L^-T T ; E = Kuf_bar .* Kuf              -> sums E [1, xs, xs^2]
+//
+// Reference arithmetic replaced: gpflow SquaredExponential.K + base_conditional as called from
+// IndependentPosteriorSingleOutputModified._conditional_fused (MixtureGPs/models.py:129-144), evaluated once
+// per point instead of once per (sample, point) (SGP.integrate only tiles X, models.py:35-36), and TF's
+// reverse pass through it (utils/training_utils.py:8-10).  Math: SURVEY.md Appendix B.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mgp {
+
+constexpr int SK_WARPS = 8;
+constexpr int SK_THREADS = SK_WARPS * 32;
+constexpr int MUB_STR = 12;  // [n][k] staging stride of mubar (conflict-free B-fragment loads)
+
+__host__ __device__ inline int xs_stride(int Dp) { return ((Dp - 4 + 15) / 16) * 16 + 4; }
+
+// 16-row block dealt to warp w in round r (snake order); returns -1 past the end
+__device__ __forceinline__ int snake_block(int round, int warp, int nb16) {
+    const int b = round * SK_WARPS + ((round & 1) ? (SK_WARPS - 1 - warp) : warp);
+    return b < nb16 ? b : -1;
+}
+
+// acc[2][NF][2] += W[rows 8*rb8 .. +16, k4-blocks kb0..kb1) * T[(kb*4 ..), :]
+// Wf points at k4-block 0 of this segment for row-block 0; C4 = total k4-blocks per row-block of W.
+// SCALED: right-operand column (nf*8+g) is multiplied by sc[nf] (diag(vbar_k) folded into the B fragment).
+template <int NT, bool SCALED>
+__device__ __forceinline__ void wgemm_block(const double* __restrict__ Wf, int C4, int rb8, int kb0, int kb1,
+                                            const double* Tsm, double (&acc)[2][NT / 8][2],
+                                            const double (&sc)[NT / 8], int lane) {
+    constexpr int NF = NT / 8, STR = NT + 4;
+    const int g = lane >> 2, t = lane & 3;
+    const double* w0 = Wf + ((size_t)rb8 * C4) * 32 + lane;
+    const double* w1 = w0 + (size_t)C4 * 32;
+    const double* tb = Tsm + t * STR + g;
+    int kb = kb0;
+    const int ngroups = (kb1 - kb0) >> 2;
+    double a0[4], a1[4];
+    if (ngroups > 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            a0[j] = __ldg(w0 + (size_t)(kb + j) * 32);
+            a1[j] = __ldg(w1 + (size_t)(kb + j) * 32);
+        }
+    }
+    for (int it = 0; it < ngroups; ++it) {
+        double n0[4], n1[4];
+        if (it + 1 < ngroups) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                n0[j] = __ldg(w0 + (size_t)(kb + 4 + j) * 32);
+                n1[j] = __ldg(w1 + (size_t)(kb + 4 + j) * 32);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double* tr = tb + (size_t)(kb + j) * 4 * STR;
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf) {
+                double b = tr[nf * 8];
+                if (SCALED) b *= sc[nf];
+                dmma(acc[0][nf], a0[j], b);
+                dmma(acc[1][nf], a1[j], b);
+            }
+        }
+        if (it + 1 < ngroups) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                a0[j] = n0[j];
+                a1[j] = n1[j];
+            }
+        }
+        kb += 4;
+    }
+    for (; kb < kb1; ++kb) {
+        const double x0 = __ldg(w0 + (size_t)kb * 32), x1 = __ldg(w1 + (size_t)kb * 32);
+        const double* tr = tb + (size_t)kb * 4 * STR;
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) {
+            double b = tr[nf * 8];
+            if (SCALED) b *= sc[nf];
+            dmma(acc[0][nf], x0, b);
+            dmma(acc[1][nf], x1, b);
+        }
+    }
+}
+
+template <int NF>
+__device__ __forceinline__ void zero_acc(double (&acc)[2][NF][2]) {
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+}
+
+// Xs[n][d] = X[n0+n][d] / lengthscale_d (0 outside the chunk / padding); xs2[n] = |Xs_n|^2
+template <int NT>
+__device__ __forceinline__ void stage_x(const LayerDev& ly, const ChunkBuffers& cb, int64_t n0, double* Xs,
+                                        double* xs2) {
+    const int Dp = ly.Dp, D = ly.D, XSTR = xs_stride(Dp);
+    for (int idx = threadIdx.x; idx < NT * Dp; idx += SK_THREADS) {
+        const int n = idx / Dp, d = idx % Dp;
+        double v = 0.0;
+        if (n0 + n < cb.n && d < D) v = cb.X[(size_t)(n0 + n) * D + d] / ly.lengthscales[ly.n_ls == 1 ? 0 : d];
+        Xs[n * XSTR + d] = v;
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < NT; n += SK_THREADS) {
+        double s = 0.0;
+        for (int d = 0; d < Dp; ++d) s += Xs[n * XSTR + d] * Xs[n * XSTR + d];
+        xs2[n] = s;
+    }
+    __syncthreads();
+}
+
+// Kuf values of the 8-row block rb8 in C-fragment layout: kv[nf][e] = k(z_{8 rb8+g}, x_{nf*8+2t+e}).
+// The -2 Zs.Xs contraction runs on DMMA (north_star: "squared-distance term on FP64 DMMA").
+template <int NT>
+__device__ __forceinline__ void gen_kuf_block(const LayerDev& ly, int rb8, const double* Xs, const double* xs2,
+                                              double variance, double (&kv)[NT / 8][2], int lane) {
+    constexpr int NF = NT / 8;
+    const int g = lane >> 2, t = lane & 3;
+    const int Dp = ly.Dp, XSTR = xs_stride(Dp), D4 = Dp >> 2;
+#pragma unroll
+    for (int nf = 0; nf < NF; ++nf) kv[nf][0] = kv[nf][1] = 0.0;
+    for (int kd = 0; kd < D4; ++kd) {
+        const double a = __ldg(ly.Zs_fm + ((size_t)rb8 * D4 + kd) * 32 + lane);
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) dmma(kv[nf], a, Xs[(nf * 8 + g) * XSTR + kd * 4 + t]);
+    }
+    const int i = rb8 * 8 + g;
+    const double zi = __ldg(ly.zs2 + i);
+    const bool live = i < ly.M;
+#pragma unroll
+    for (int nf = 0; nf < NF; ++nf)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double r2 = -2.0 * kv[nf][e] + (zi + xs2[nf * 8 + 2 * t + e]);   // square_distance(X, X2)
+            kv[nf][e] = live ? variance * exp(-0.5 * r2) : 0.0;                    // K_r2
+        }
+}
+
+// T[:, 0..NT) <- G[:, n0 .. n0+NT)  for a row-major [Mp, ldn] array (16-byte cp.async)
+template <int NT>
+__device__ __forceinline__ void load_tile_async(double* T, const double* G, int Mp, int64_t ldn, int64_t n0) {
+    constexpr int STR = NT + 4, C2 = NT / 2;
+    for (int idx = threadIdx.x; idx < Mp * C2; idx += SK_THREADS) {
+        const int row = idx / C2, c2 = idx % C2;
+        cp_async16(T + (size_t)row * STR + 2 * c2, G + (size_t)row * ldn + n0 + 2 * c2);
+    }
+    cp_async_commit();
+}
+
+// ==================================================================================================
+// cond_fwd_a
+// ==================================================================================================
+template <int NT>
+__global__ void __launch_bounds__(SK_THREADS) cond_fwd_a_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
+    constexpr int NF = NT / 8, STR = NT + 4;
+    extern __shared__ __align__(16) double smem[];
+    const int Mp = ly.Mp, XSTR = xs_stride(ly.Dp);
+    double* T = smem;
+    double* Xs = T + (size_t)Mp * STR;
+    double* xs2 = Xs + NT * XSTR;
+    double* colpart = xs2 + NT;  // [SK_WARPS][NT]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int nb16 = Mp / 16, nb8 = Mp / 8, C4 = Mp / 4;
+    const double variance = ly.variance[0];
+    const double sc_dummy[NF] = {};
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t n0 = (int64_t)tile * NT;
+        stage_x<NT>(ly, cb, n0, Xs, xs2);
+        for (int rb = warp; rb < nb8; rb += SK_WARPS) {
+            double kv[NF][2];
+            gen_kuf_block<NT>(ly, rb, Xs, xs2, variance, kv, lane);
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf)
+                *reinterpret_cast<double2*>(T + (size_t)(rb * 8 + g) * STR + nf * 8 + 2 * t) = make_double2(kv[nf][0], kv[nf][1]);
+        }
+        __syncthreads();
+        double colsq[NF][2];
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) colsq[nf][0] = colsq[nf][1] = 0.0;
+        for (int round = 0; round * SK_WARPS < nb16; ++round) {
+            const int b = snake_block(round, warp, nb16);
+            if (b < 0) continue;
+            double acc[2][NF][2];
+            zero_acc<NF>(acc);
+            wgemm_block<NT, false>(ly.W_Linv, C4, 2 * b, 0, (b + 1) * 4, T, acc, sc_dummy, lane);   // lower triangular
+#pragma unroll
+            for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) {
+                    const size_t row = (size_t)(b * 16 + mf * 8 + g);
+                    *reinterpret_cast<double2*>(cb.A + row * cb.ldn + n0 + nf * 8 + 2 * t) =
+                        make_double2(acc[mf][nf][0], acc[mf][nf][1]);
+                    colsq[nf][0] += acc[mf][nf][0] * acc[mf][nf][0];
+                    colsq[nf][1] += acc[mf][nf][1] * acc[mf][nf][1];
+                }
+        }
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double s = sum_over_g(colsq[nf][e]);
+                if (g == 0) colpart[warp * NT + nf * 8 + 2 * t + e] = s;
+            }
+        __syncthreads();
+        for (int n = threadIdx.x; n < NT; n += SK_THREADS) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < SK_WARPS; ++w) s += colpart[w * NT + n];
+            cb.asq[n0 + n] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// ==================================================================================================
+// cond_fwd_b
+// ==================================================================================================
+template <int NT>
+__global__ void __launch_bounds__(SK_THREADS) cond_fwd_b_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
+    constexpr int NF = NT / 8, STR = NT + 4;
+    extern __shared__ __align__(16) double smem[];
+    const int Mp = ly.Mp, K = ly.K;
+    double* T = smem;
+    double* colpart = T + (size_t)Mp * STR;  // [SK_WARPS][KP][NT]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int nb16 = Mp / 16, C4 = Mp / 4;
+    const double variance = ly.variance[0];
+    const double sc_dummy[NF] = {};
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t n0 = (int64_t)tile * NT;
+        load_tile_async<NT>(T, cb.A, Mp, cb.ldn, n0);
+        cp_async_wait<0>();
+        __syncthreads();
+        for (int k = 0; k < K; ++k) {
+            double colsq[NF][2];
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf) colsq[nf][0] = colsq[nf][1] = 0.0;
+            const double* Wk = ly.W_LqT + (size_t)k * Mp * Mp;
+            for (int round = 0; round * SK_WARPS < nb16; ++round) {
+                const int b = snake_block(round, warp, nb16);
+                if (b < 0) continue;
+                double acc[2][NF][2];
+                zero_acc<NF>(acc);
+                wgemm_block<NT, false>(Wk, C4, 2 * b, b * 4, C4, T, acc, sc_dummy, lane);   // upper triangular
+#pragma unroll
+                for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf) {
+                        colsq[nf][0] += acc[mf][nf][0] * acc[mf][nf][0];
+                        colsq[nf][1] += acc[mf][nf][1] * acc[mf][nf][1];
+                    }
+            }
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double s = sum_over_g(colsq[nf][e]);
+                    if (g == 0) colpart[((size_t)warp * KP + k) * NT + nf * 8 + 2 * t + e] = s;
+                }
+        }
+        if (warp == SK_WARPS - 1) {  // fmean^T [K x NT] = q_mu^T [K x Mp] * A tile
+            double acc[2][NF][2];
+            zero_acc<NF>(acc);
+            wgemm_block<NT, false>(ly.W_mT, C4, 0, 0, C4, T, acc, sc_dummy, lane);
+            if (g < K) {
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+                        cb.fmean[(size_t)(n0 + nf * 8 + 2 * t + e) * K + g] = acc[0][nf][e];
+            }
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < NT * K; idx += SK_THREADS) {
+            const int n = idx / K, k = idx % K;
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < SK_WARPS; ++w) s += colpart[((size_t)w * KP + k) * NT + n];
+            cb.fvar[(size_t)(n0 + n) * K + k] = (variance - cb.asq[n0 + n]) + s;   // Knn - sum A^2 + sum LTA^2
+        }
+        __syncthreads();
+    }
+}
+
+// ==================================================================================================
+// cond_bwd_a
+// ==================================================================================================
+template <int NT>
+__global__ void __launch_bounds__(SK_THREADS) cond_bwd_a_kernel(LayerDev ly, ChunkBuffers cb, int ntiles,
+                                                                double* mraw_part) {
+    constexpr int NF = NT / 8, STR = NT + 4;
+    extern __shared__ __align__(16) double smem[];
+    const int Mp = ly.Mp, K = ly.K;
+    double* T = smem;
+    double* mubT = T + (size_t)Mp * STR;  // [KP][STR]   mubar^T (right operand of the q_mu segment)
+    double* mubN = mubT + KP * STR;       // [NT][MUB_STR] mubar (right operand of A mubar)
+    double* vb = mubN + NT * MUB_STR;     // [KP][NT]    vbar^T
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int nb16 = Mp / 16, C4 = Mp / 4, C4tot = (K * Mp + KP) / 4;
+    double* my_part = mraw_part + (size_t)blockIdx.x * Mp * KP;
+    const double sc_dummy[NF] = {};
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t n0 = (int64_t)tile * NT;
+        load_tile_async<NT>(T, cb.A, Mp, cb.ldn, n0);
+        for (int idx = threadIdx.x; idx < NT * KP; idx += SK_THREADS) {
+            const int n = idx / KP, k = idx % KP;
+            const double mv = k < K ? cb.mubar[(size_t)(n0 + n) * K + k] : 0.0;
+            const double vv = k < K ? cb.vbar[(size_t)(n0 + n) * K + k] : 0.0;
+            mubT[k * STR + n] = mv;
+            mubN[n * MUB_STR + k] = mv;
+            vb[k * NT + n] = vv;
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        for (int round = 0; round * SK_WARPS < nb16; ++round) {
+            const int b = snake_block(round, warp, nb16);
+            if (b < 0) continue;
+            // (1) q_mu gradient partial: (A mubar)[rows, k] over this tile's points
+            {
+                double am[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+                for (int ks = 0; ks < NT / 4; ++ks) {
+                    const double bb = mubN[(ks * 4 + t) * MUB_STR + g];
+#pragma unroll
+                    for (int mf = 0; mf < 2; ++mf)
+                        dmma(am[mf], T[(size_t)(b * 16 + mf * 8 + g) * STR + ks * 4 + t], bb);
+                }
+#pragma unroll
+                for (int mf = 0; mf < 2; ++mf) {
+                    double* p = my_part + (size_t)(b * 16 + mf * 8 + g) * KP + 2 * t;
+                    p[0] += am[mf][0];
+                    p[1] += am[mf][1];
+                }
+            }
+            // (2) Abar rows
+            double acc[2][NF][2];
+            zero_acc<NF>(acc);
+            for (int k = 0; k < K; ++k) {
+                double sc[NF];
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) sc[nf] = vb[k * NT + nf * 8 + g];
+                wgemm_block<NT, true>(ly.W_Q + (size_t)k * C4 * 32, C4tot, 2 * b, 0, C4, T, acc, sc, lane);
+            }
+            wgemm_block<NT, false>(ly.W_Q + (size_t)K * C4 * 32, C4tot, 2 * b, 0, KP / 4, mubT, acc, sc_dummy, lane);
+#pragma unroll
+            for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) {
+                    const size_t row = (size_t)(b * 16 + mf * 8 + g);
+                    *reinterpret_cast<double2*>(cb.A + row * cb.ldn + n0 + nf * 8 + 2 * t) =
+                        make_double2(acc[mf][nf][0], acc[mf][nf][1]);
+                }
+        }
+        __syncthreads();
+    }
+}
+
+// ==================================================================================================
+// cond_bwd_b
+// ==================================================================================================
+template <int NT>
+__global__ void __launch_bounds__(SK_THREADS) cond_bwd_b_kernel(LayerDev ly, ChunkBuffers cb, int ntiles,
+                                                                double* esum_part) {
+    constexpr int NF = NT / 8, STR = NT + 4;
+    extern __shared__ __align__(16) double smem[];
+    const int Mp = ly.Mp, Dp = ly.Dp, D = ly.D, XSTR = xs_stride(Dp), E = 1 + 2 * Dp;
+    double* T = smem;
+    double* Xs = T + (size_t)Mp * STR;
+    double* xs2 = Xs + NT * XSTR;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int nb16 = Mp / 16, C4 = Mp / 4;
+    const double variance = ly.variance[0];
+    double* my_part = esum_part + (size_t)blockIdx.x * Mp * E;
+    const double sc_dummy[NF] = {};
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t n0 = (int64_t)tile * NT;
+        load_tile_async<NT>(T, cb.A, Mp, cb.ldn, n0);
+        stage_x<NT>(ly, cb, n0, Xs, xs2);
+        cp_async_wait<0>();
+        __syncthreads();
+        for (int round = 0; round * SK_WARPS < nb16; ++round) {
+            const int b = snake_block(round, warp, nb16);
+            if (b < 0) continue;
+            double acc[2][NF][2];
+            zero_acc<NF>(acc);
+            wgemm_block<NT, false>(ly.W_LinvT, C4, 2 * b, b * 4, C4, T, acc, sc_dummy, lane);   // upper triangular
+#pragma unroll
+            for (int mf = 0; mf < 2; ++mf) {
+                double kv[NF][2];
+                gen_kuf_block<NT>(ly, 2 * b + mf, Xs, xs2, variance, kv, lane);
+                double e0 = 0.0;
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        acc[mf][nf][e] *= kv[nf][e];   // E = Kuf_bar .* Kuf
+                        e0 += acc[mf][nf][e];
+                    }
+                double* p = my_part + (size_t)(b * 16 + mf * 8 + g) * E;
+                e0 = sum_over_t(e0);
+                if (t == 0) p[0] += e0;
+                for (int d = 0; d < D; ++d) {
+                    double e1 = 0.0, e2 = 0.0;
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const double x = Xs[(nf * 8 + 2 * t + e) * XSTR + d];
+                            const double ex = acc[mf][nf][e] * x;
+                            e1 += ex;
+                            e2 += ex * x;
+                        }
+                    e1 = sum_over_t(e1);
+                    e2 = sum_over_t(e2);
+                    if (t == 0) {
+                        p[1 + d] += e1;
+                        p[1 + Dp + d] += e2;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ==================================================================================================
+// host side
+// ==================================================================================================
+int stream_max_parts(const Launch& ln) { return ln.num_sms * 4; }
+
+static int pick_nt(int Mp, size_t extra_bytes_nt32) {
+    // widest supported tile whose [Mp x (NT+4)] operand fits in 227 KB (Mp=256, NT=32: 74 KB -> 3 CTAs/SM)
+    const size_t cap = 227 * 1024;
+    if ((size_t)Mp * 36 * 8 + extra_bytes_nt32 <= cap) return 32;
+    if ((size_t)Mp * 20 * 8 + extra_bytes_nt32 <= cap) return 16;
+    return 0;
+}
+
+template <typename KernelT>
+static int persistent_grid(KernelT kernel, size_t smem, int ntiles, int cap, const Launch& ln) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, SK_THREADS, smem);
+    if (occ < 1) occ = 1;
+    int grid = ln.num_sms * occ;
+    if (grid > ntiles) grid = ntiles;
+    if (cap > 0 && grid > cap) grid = cap;
+    return grid < 1 ? 1 : grid;
+}
+
+void cond_fwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
+    const int XSTR = xs_stride(ly.Dp);
+    const int nt = pick_nt(ly.Mp, (size_t)(32 * XSTR + 32 + SK_WARPS * 32) * 8);
+    auto launch = [&](auto kernel, int NT) {
+        const size_t smem = ((size_t)ly.Mp * (NT + 4) + NT * XSTR + NT + SK_WARPS * NT) * sizeof(double);
+        const int ntiles = (int)((cb.n + NT - 1) / NT);
+        const int grid = persistent_grid(kernel, smem, ntiles, 0, ln);
+        kernel<<<grid, SK_THREADS, smem, ln.stream>>>(ly, cb, ntiles);
+        ln.tick();
+    };
+    if (nt == 32) launch(cond_fwd_a_kernel<32>, 32); else launch(cond_fwd_a_kernel<16>, 16);
+}
+
+void cond_fwd_b(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
+    const int nt = pick_nt(ly.Mp, (size_t)(SK_WARPS * KP * 32) * 8);
+    auto launch = [&](auto kernel, int NT) {
+        const size_t smem = ((size_t)ly.Mp * (NT + 4) + (size_t)SK_WARPS * KP * NT) * sizeof(double);
+        const int ntiles = (int)((cb.n + NT - 1) / NT);
+        const int grid = persistent_grid(kernel, smem, ntiles, 0, ln);
+        kernel<<<grid, SK_THREADS, smem, ln.stream>>>(ly, cb, ntiles);
+        ln.tick();
+    };
+    if (nt == 32) launch(cond_fwd_b_kernel<32>, 32); else launch(cond_fwd_b_kernel<16>, 16);
+}
+
+void cond_bwd_a(const LayerDev& ly, const ChunkBuffers& cb, double* mraw_part, int nparts_cap, int* nparts,
+                const Launch& ln) {
+    const int nt = pick_nt(ly.Mp, (size_t)(KP * 36 + 32 * MUB_STR + KP * 32) * 8);
+    auto launch = [&](auto kernel, int NT) {
+        const size_t smem = ((size_t)ly.Mp * (NT + 4) + KP * (NT + 4) + NT * MUB_STR + KP * NT) * sizeof(double);
+        const int ntiles = (int)((cb.n + NT - 1) / NT);
+        const int grid = persistent_grid(kernel, smem, ntiles, nparts_cap, ln);
+        kernel<<<grid, SK_THREADS, smem, ln.stream>>>(ly, cb, ntiles, mraw_part);
+        ln.tick();
+        if (grid > *nparts) *nparts = grid;
+    };
+    if (nt == 32) launch(cond_bwd_a_kernel<32>, 32); else launch(cond_bwd_a_kernel<16>, 16);
+}
+
+void cond_bwd_b(const LayerDev& ly, const ChunkBuffers& cb, double* esum_part, int nparts_cap, int* nparts,
+                const Launch& ln) {
+    const int XSTR = xs_stride(ly.Dp);
+    const int nt = pick_nt(ly.Mp, (size_t)(32 * XSTR + 32) * 8);
+    auto launch = [&](auto kernel, int NT) {
+        const size_t smem = ((size_t)ly.Mp * (NT + 4) + NT * XSTR + NT) * sizeof(double);
+        const int ntiles = (int)((cb.n + NT - 1) / NT);
+        const int grid = persistent_grid(kernel, smem, ntiles, nparts_cap, ln);
+        kernel<<<grid, SK_THREADS, smem, ln.stream>>>(ly, cb, ntiles, esum_part);
+        ln.tick();
+        if (grid > *nparts) *nparts = grid;
+    };
+    if (nt == 32) launch(cond_bwd_b_kernel<32>, 32); else launch(cond_bwd_b_kernel<16>, 16);
+}
+
+}  // namespace mgp

@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Headline benchmark: ELBO forward+backward points/s of the SVGP mixture at BASELINE.json config #4
+(N = 2^20 points in total, D = 2, M = 256 inducing points per layer, K = 4 components, S = 16 MC samples),
+float64, synthetic data, on 1/2/4/8 B200 of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] ...                # the reference arm: CPU restatement on host cores
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = everything needed to hand an optimiser -ELBO and all its gradients: Kuu build +
+Cholesky of both layers, the streamed conditional forward, the fused MC pass, the full backward, the single
+all-reduce (N > 1) and the replicated Cholesky/kernel backward.  Rank 0 prints ONE JSON line.
+
+  value   whole-job points/s with X, Y resident in HBM            (device-timed, max over ranks)
+  e2e     the same metric through the public Python API with HOST (pinned) X, Y: H2D copy of the step's inputs
+          and a D2H read of the loss inside the timed region
+  roofline  the dominant kernel against the measured FP64 DMMA peak (profiles/r01_fp64_peak_microbench.txt);
+            MEASURED_PEAKS.json holds HBM and bf16 peaks only, so the FP64 denominator is this repo's own
+            measurement on the same pool, stated in the object
+  cpu_baseline  oracle/svgp_mixture.py (the CPU float64 restatement of the TF2/GPflow path; TF itself is not
+            installable in this image) timed on the box's host cores on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_TOTAL = 1 << 20
+D, M, K, S = 2, 256, 4, 16
+FP64_PEAK_TFLOPS = 37.0      # measured DMMA.8x8x4 issue-rate peak on this pool's B200 (profiles/r01_fp64_peak_microbench.txt)
+DGEMM_TFLOPS = 35.4          # cuBLAS DGEMM 8192^3 on the same box (profiles/r01_dgemm_peak.json)
+
+
+def flops_per_point(m=M, k=K, d=D):
+    """algorithmic flops per point, two layers, forward + backward."""
+    return 6 * (k + 1) * m * m + 12 * m * (d + 2 * k + 1)
+
+
+def make_workload(n_points, seed=0, m=M, k=K, d=D):
+    """Config #4 synthetic inputs and parameters."""
+    rng = np.random.default_rng(seed)
+    side = int(round(math.sqrt(m)))
+    X = rng.uniform(0.0, float(side), (n_points, d))
+    comp = rng.integers(0, k, n_points)
+    r1 = np.random.default_rng(1)
+    om, ph = r1.uniform(0.5, 1.5, (k, d)), r1.uniform(0, 2 * np.pi, k)
+    Y = (np.sin((X * om[comp]).sum(1) + ph[comp]) + 1.5 * comp + 0.1 * rng.standard_normal(n_points))[:, None]
+    r2 = np.random.default_rng(2)
+    g = np.linspace(0.5, side - 0.5, side)
+    grid = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, d)
+
+    def layer(var, ls):
+        Z = grid + r2.uniform(-0.2, 0.2, grid.shape)
+        q = np.stack([np.eye(m) + 0.05 * np.tril(r2.standard_normal((m, m))) for _ in range(k)])
+        idx = np.arange(m)
+        q[:, idx, idx] = np.abs(q[:, idx, idx]) + 0.05
+        return {"variance": np.float64(var), "lengthscales": np.asarray(ls, dtype=np.float64), "Z": Z,
+                "q_mu": 0.3 * r2.standard_normal((m, k)), "q_sqrt": q}
+
+    case = {"model": "SMGP", "lik": "gaussian", "K": k, "S": S, "num_data": float(N_TOTAL),
+            "pred": layer(1.0, [1.0] * d), "assign": layer(0.5, [1.5] * d), "lik_var": 0.1 + 0.05 * np.arange(k),
+            "assign_lik_var": None}
+    return case, X, Y
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement on the host cores (reported baseline, and `--impl reference`)
+# ----------------------------------------------------------------------------------------------------
+def cpu_points_per_s(chunk=4096, reps=3, warmup=1):
+    import torch
+    from oracle import svgp_mixture as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    case, X, Y = make_workload(chunk, seed=0)
+    rng = np.random.default_rng(3)
+    z = rng.standard_normal((S, chunk, K))
+    u = rng.uniform(np.finfo(np.float64).tiny, 1.0, (S, chunk, K))
+    pred, assign = O.layer_from_numpy(case["pred"]), O.layer_from_numpy(case["assign"])
+    times = []
+    for it in range(warmup + reps):
+        t0 = time.perf_counter()
+        O.elbo_and_grads("SMGP", "gaussian", pred, assign, O.as_t(case["lik_var"]), None, X, Y, z, u, case["num_data"],
+                         n_total=N_TOTAL)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return chunk / statistics.median(times), cores, times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    chunk = 8192
+    value, cores, times = cpu_points_per_s(chunk=chunk, reps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    sample = (f"{chunk} of the {N_TOTAL} config-#4 points per step, ELBO fwd+bwd (torch autograd) of oracle/svgp_mixture.py, "
+              f"explicit noise, {cores} torch threads")
+    line = {"impl": "reference", "metric": "elbo_fwd_bwd_points_per_s", "value": value, "unit": "points/s",
+            "n_gpus": args.gpus, "steps": len(times), "warmup": max(1, min(args.warmup, 2)),
+            "ms_per_step": 1e3 * statistics.median(times), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "CPU restatement of the TF2/GPflow path; TensorFlow/GPflow are not installable in this image"},
+            "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE config #4: synthetic N=2^20 (total), D=2, M=256, K=4, S=16, SMGP + GaussianModified, "
+                        "ELBO fwd+bwd step, Philox noise on device",
+            "N": N_TOTAL, "D": D, "M": M, "K": K, "S": S, "points_per_gpu": N_TOTAL // n_gpus,
+            "sharding": f"dp{n_gpus}: contiguous row shards, parameters replicated, one all-reduce of the flat reduce buffer",
+            "l2": "no explicit flush: each step streams the materialised A (2 layers x M x N/gpus x 8 B = "
+                  f"{2 * M * (N_TOTAL // n_gpus) * 8 / 1e9:.1f} GB) through HBM, far beyond the 126 MB L2"}
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.strip().split(", ") for r in open(self.tmp.name) if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, reasons, power = [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                out["sm_max_mhz"] = float(r[2])
+                power.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            busy = [c for c, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+            out["sm_mhz"] = statistics.median(busy)
+            out["power_w_max"] = max(power)
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--points", type=int, default=N_TOTAL, help="total points (default: the config-#4 size)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: modulatedgps_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world:
+        if rank == 0:
+            print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    n_total = args.points
+    n_local = n_total // world
+    n_total = n_local * world
+
+    import modulatedgps_b200 as mg  # noqa: F401
+    from modulatedgps_b200 import _lib
+    from tests.helpers_gpu import build_model
+
+    case, X, Y = make_workload(n_total, seed=0)
+    case["num_data"] = float(n_total)
+    sl = slice(rank * n_local, (rank + 1) * n_local)
+    Xh = torch.as_tensor(X[sl]).contiguous().pin_memory()
+    Yh = torch.as_tensor(Y[sl]).contiguous().pin_memory()
+    Xd, Yd = Xh.to(dev), Yh.to(dev)
+    model = build_model(case)
+    model.seed = 3
+    if world > 1:
+        model.enable_data_parallel()
+    ctx = _lib.get_context(dev)
+    kw = dict(n_global=n_total, point_offset=rank * n_local)
+
+    def step(xd, yd):
+        for v in model.trainable_variables:
+            v.grad = None
+        loss = model._training_loss((xd, yd), **kw)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input timing -------------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        step(Xd, Yd)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.timing_enable(True)
+    ctx.timing_read(reset=True)
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(Xd, Yd)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms) / args.steps
+    stages = ctx.timing_read(reset=True)
+    ctx.timing_enable(False)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(loss)
+
+    # ---- end-to-end timing: host buffers in, loss out ------------------------------------------------
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    e2.record()
+    for _ in range(args.steps):
+        xd = Xh.to(dev, non_blocking=True)
+        yd = Yh.to(dev, non_blocking=True)
+        loss = step(xd, yd)
+        _ = loss.item()
+    e3.record()
+    barrier()
+    t_host = time.perf_counter() - t_host0
+    ms2 = torch.tensor([max(e2.elapsed_time(e3), 0.0)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2) / args.steps
+
+    if rank == 0:
+        value = n_total / (ms_per_step * 1e-3)
+        per_stage = {k: (v[0] / args.steps) for k, v in stages.items()}
+        # dominant kernel and its algorithmic flops per step on this rank (per layer:
+        # cond_fwd_a M^2, cond_fwd_b K M^2, syrk K M^2, cond_bwd_a K M^2, cond_bwd_b M^2 (+ the M^2 of the L-bar
+        # reduction, which this design folds into the S_k algebra); x2 layers)
+        alg = {"cond_fwd_a": 2 * M * M, "cond_fwd_b": 2 * K * M * M, "syrk": 2 * K * M * M, "cond_bwd_a": 2 * K * M * M,
+               "cond_bwd_b": 2 * 2 * M * M}
+        executed = {"cond_fwd_a": 2 * M * M * 17 / 16, "cond_fwd_b": 2 * K * M * M * 17 / 16, "syrk": 2 * K * M * M * 40960 / 32896,
+                    "cond_bwd_a": 2 * 2 * K * M * M, "cond_bwd_b": 2 * M * M * 17 / 16}
+        dom = max(alg, key=lambda k: per_stage.get(k, 0.0))
+        dom_ms = per_stage[dom]
+        achieved = alg[dom] * n_local / (dom_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                    "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                    "executed_tflops": executed[dom] * n_local / (dom_ms * 1e-3) / 1e12,
+                    "peak_source": "FP64 DMMA issue-rate peak measured on this pool's B200 by tools/fp64_peak.cu "
+                                   "(profiles/r01_fp64_peak_microbench.txt); MEASURED_PEAKS.json has no FP64 entry; "
+                                   f"cuBLAS DGEMM on the same box: {DGEMM_TFLOPS} TFLOP/s",
+                    "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms_per_step}
+        step_roof_ms = flops_per_point() * n_local / (FP64_PEAK_TFLOPS * 1e12) * 1e3
+        line = {"metric": "elbo_fwd_bwd_points_per_s", "value": value, "unit": "points/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(world), "clocks": clocks,
+                "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
+                        "host_wall_ms_per_step": 1e3 * t_host / args.steps,
+                        "h2d_bytes_per_step": int(Xh.numel() * 8 + Yh.numel() * 8) * world, "d2h_bytes_per_step": 8 * world,
+                        "api": "modulatedgps_b200.SMGP._training_loss((X_host, Y_host)) + loss.backward() + loss.item()"},
+                "gpu_launches": int(launches), "roofline": roofline,
+                "step_roofline": {"flops_per_point": flops_per_point(), "roof_ms_per_step": step_roof_ms,
+                                  "frac_of_fp64_peak": step_roof_ms / ms_per_step, "peak_tflops": FP64_PEAK_TFLOPS},
+                "stages_ms_per_step": per_stage, "loss": final_loss}
+        if not args.no_cpu_baseline and world == 1:
+            v, cores, times = cpu_points_per_s(chunk=4096, reps=3, warmup=1)
+            line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": cores, "kind": "port",
+                                    "sample": f"4096 of the {N_TOTAL} config-#4 points, 3 timed repetitions after 1 warm-up, "
+                                              "oracle/svgp_mixture.py ELBO fwd+bwd (torch CPU autograd, explicit noise)",
+                                    "note": "CPU restatement of the TF2/GPflow path; TF/GPflow are not installable here"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -88,6 +88,13 @@ int64_t mgp_launch_count(const mgp_ctx* ctx);
 /* Synchronises the stream and reports deferred device-side failures (MGP_ERR_NOT_PD when a Cholesky pivot
  * was not positive since the last check; MGP_ERR_CUDA for asynchronous CUDA errors). */
 int mgp_check_status(mgp_ctx* ctx);
+/* Optional per-stage device timing (CUDA events on the launch stream around each kernel group).  Off by default;
+ * bench.py switches it on for the timed region to report the live roofline of the dominant kernel.
+ * mgp_timing_read synchronises the stream; ms/calls have mgp_num_stages() entries, named by mgp_stage_name. */
+int mgp_timing_enable(mgp_ctx* ctx, int on);
+int mgp_timing_read(mgp_ctx* ctx, double* ms, int64_t* calls, int reset);
+int mgp_num_stages(void);
+const char* mgp_stage_name(int i);
 /* cap for the per-call point chunk (0 = automatic: whole shard if the materialised A fits the budget) */
 int mgp_set_chunk_points(mgp_ctx* ctx, int64_t max_points);
 

@@ -61,6 +61,10 @@ _PROTOTYPES = {
     "mgp_launch_count": (C.c_int64, [C.c_void_p]),
     "mgp_check_status": (C.c_int, [C.c_void_p]),
     "mgp_set_chunk_points": (C.c_int, [C.c_void_p, C.c_int64]),
+    "mgp_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "mgp_timing_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
+    "mgp_num_stages": (C.c_int, []),
+    "mgp_stage_name": (C.c_char_p, [C.c_int]),
     "mgp_svgp_predict_f": (C.c_int, [C.c_void_p, C.POINTER(MgpLayer), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "mgp_prior_kl": (C.c_int, [C.c_void_p, C.POINTER(MgpLayer), C.c_void_p]),
     "mgp_predict_y": (C.c_int, [C.c_void_p, C.POINTER(MgpLayer), C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
@@ -137,6 +141,17 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.mgp_launch_count(self.handle))
+
+    def timing_enable(self, on: bool):
+        self.check(self.lib.mgp_timing_enable(self.handle, 1 if on else 0))
+
+    def timing_read(self, reset: bool = True):
+        """{stage name: (milliseconds, launches-groups)} accumulated since the last reset (synchronises)."""
+        n = int(self.lib.mgp_num_stages())
+        ms = (C.c_double * n)()
+        calls = (C.c_int64 * n)()
+        self.check(self.lib.mgp_timing_read(self.handle, ms, calls, 1 if reset else 0))
+        return {self.lib.mgp_stage_name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(n)}
 
     def set_chunk_points(self, n: int):
         self.check(self.lib.mgp_set_chunk_points(self.handle, int(n)))

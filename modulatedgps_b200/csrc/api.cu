@@ -32,7 +32,47 @@ struct LayerSlot {
 
 }  // namespace
 
+enum Stage { ST_PRECOMPUTE = 0, ST_COND_FWD_A, ST_COND_FWD_B, ST_MC_PASS, ST_SYRK, ST_COND_BWD_A, ST_COND_BWD_B,
+             ST_REDUCE, ST_FINISH, ST_COUNT };
+static const char* const kStageNames[ST_COUNT] = {"precompute", "cond_fwd_a", "cond_fwd_b", "mc_pass", "syrk",
+                                                  "cond_bwd_a", "cond_bwd_b", "reduce_partials", "finish"};
+
+// Optional per-stage device timing with CUDA events on the launch stream (bench.py's live roofline numbers).
+struct StageTimer {
+    bool on = false;
+    struct Rec { int stage; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    double ms[ST_COUNT] = {};
+    int64_t calls[ST_COUNT] = {};
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void begin(int stage, cudaStream_t st) {
+        if (!on) return;
+        Rec r{stage, get(), get()};
+        cudaEventRecord(r.a, st);
+        recs.push_back(r);
+    }
+    void end(cudaStream_t st) {
+        if (!on) return;
+        cudaEventRecord(recs.back().b, st);
+    }
+    void collect(cudaStream_t st) {
+        if (recs.empty()) return;
+        cudaStreamSynchronize(st);
+        for (auto& r : recs) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.stage] += t; calls[r.stage] += 1; }
+            pool.push_back(r.a); pool.push_back(r.b);
+        }
+        recs.clear();
+    }
+};
+
 struct mgp_ctx {
+    StageTimer timer;
     int device = 0;
     cudaStream_t stream = nullptr;
     int num_sms = 0;
@@ -170,6 +210,12 @@ ChunkBuffers chunk_of(const LayerSlot& s, const double* X, int64_t n, int64_t ld
 
 Launch launch_of(mgp_ctx* c) { return Launch{c->stream, &c->launches, c->num_sms}; }
 
+struct Timed {   // RAII stage bracket
+    mgp_ctx* c;
+    Timed(mgp_ctx* ctx, int stage) : c(ctx) { c->timer.begin(stage, c->stream); }
+    ~Timed() { c->timer.end(c->stream); }
+};
+
 // points per chunk so that the materialised A of `nlayers` layers fits the budget
 int64_t pick_chunk(mgp_ctx* c, int64_t N, int Mp_max, int nlayers) {
     int64_t cap = c->chunk_cap;
@@ -283,6 +329,25 @@ int mgp_set_chunk_points(mgp_ctx* c, int64_t max_points) {
     c->chunk_cap = max_points;
     return MGP_OK;
 }
+
+int mgp_timing_enable(mgp_ctx* c, int on) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    c->timer.collect(c->stream);
+    c->timer.on = on != 0;
+    return MGP_OK;
+}
+
+int mgp_timing_read(mgp_ctx* c, double* ms, int64_t* calls, int reset) {
+    if (!c || !ms || !calls) return MGP_ERR_BAD_ARG;
+    c->timer.collect(c->stream);
+    for (int i = 0; i < ST_COUNT; ++i) { ms[i] = c->timer.ms[i]; calls[i] = c->timer.calls[i]; }
+    if (reset) for (int i = 0; i < ST_COUNT; ++i) { c->timer.ms[i] = 0.0; c->timer.calls[i] = 0; }
+    return MGP_OK;
+}
+
+int mgp_num_stages(void) { return ST_COUNT; }
+
+const char* mgp_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageNames[i] : ""; }
 
 int mgp_check_status(mgp_ctx* c) {
     if (!c) return MGP_ERR_BAD_ARG;
@@ -405,8 +470,11 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
     const LayerRB ra = layer_rb(rp.end, sa.dev.Mp, sa.dev.Dp, K);
     CUDA_TRY(c, cudaMemsetAsync(reduce_buf, 0, sizeof(double) * ra.end, c->stream));
 
-    precompute_layer(sp.dev, true, (int*)c->status.p, ln);
-    precompute_layer(sa.dev, true, (int*)c->status.p, ln);
+    {
+        Timed t(c, ST_PRECOMPUTE);
+        precompute_layer(sp.dev, true, (int*)c->status.p, ln);
+        precompute_layer(sa.dev, true, (int*)c->status.p, ln);
+    }
     c->pre_valid = true;
     if (N_local == 0) return MGP_OK;   // an empty shard contributes zeros
 
@@ -435,10 +503,10 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
         const int64_t n = (N_local - c0 < Nc) ? N_local - c0 : Nc;
         const int64_t ldc = round_up64(n, 64);   // padded extent of THIS chunk (<= ldn); leading dimension stays ldn
         ChunkBuffers cp = chunk_of(sp, X + c0 * D, n, ldn), ca = chunk_of(sa, X + c0 * D, n, ldn);
-        cond_fwd_a(sp.dev, cp, ln);
-        cond_fwd_b(sp.dev, cp, ln);
-        cond_fwd_a(sa.dev, ca, ln);
-        cond_fwd_b(sa.dev, ca, ln);
+        { Timed t(c, ST_COND_FWD_A); cond_fwd_a(sp.dev, cp, ln); }
+        { Timed t(c, ST_COND_FWD_B); cond_fwd_b(sp.dev, cp, ln); }
+        { Timed t(c, ST_COND_FWD_A); cond_fwd_a(sa.dev, ca, ln); }
+        { Timed t(c, ST_COND_FWD_B); cond_fwd_b(sa.dev, ca, ln); }
         McArgs m;
         m.model = cfg->model; m.lik = cfg->lik; m.S = cfg->S; m.K = K;
         m.temperature = cfg->temperature;
@@ -449,16 +517,20 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
         m.mubar_p = cp.mubar; m.vbar_p = cp.vbar; m.mubar_a = ca.mubar; m.vbar_a = ca.vbar;
         m.lik_var = lik_var; m.assign_lik_var = assign_lik_var;
         m.z = noise->z; m.u = noise->u; m.seed = noise->seed; m.point_offset = noise->point_offset;
-        mc_pass(m, (double*)c->mc_part.p, ln);
-        mc_fold((double*)c->mc_part.p, mc_num_blocks(ldc), reduce_buf, ln);
-        syrk_accumulate(sp.dev, cp, (double*)sp.syrk_part.p, sp.nsplit, ln);
-        syrk_accumulate(sa.dev, ca, (double*)sa.syrk_part.p, sa.nsplit, ln);
-        cond_bwd_a(sp.dev, cp, (double*)sp.mraw_part.p, maxparts, &sp.mraw_nparts, ln);
-        cond_bwd_b(sp.dev, cp, (double*)sp.esum_part.p, maxparts, &sp.esum_nparts, ln);
-        cond_bwd_a(sa.dev, ca, (double*)sa.mraw_part.p, maxparts, &sa.mraw_nparts, ln);
-        cond_bwd_b(sa.dev, ca, (double*)sa.esum_part.p, maxparts, &sa.esum_nparts, ln);
+        {
+            Timed t(c, ST_MC_PASS);
+            mc_pass(m, (double*)c->mc_part.p, ln);
+            mc_fold((double*)c->mc_part.p, mc_num_blocks(ldc), reduce_buf, ln);
+        }
+        { Timed t(c, ST_SYRK); syrk_accumulate(sp.dev, cp, (double*)sp.syrk_part.p, sp.nsplit, ln); }
+        { Timed t(c, ST_SYRK); syrk_accumulate(sa.dev, ca, (double*)sa.syrk_part.p, sa.nsplit, ln); }
+        { Timed t(c, ST_COND_BWD_A); cond_bwd_a(sp.dev, cp, (double*)sp.mraw_part.p, maxparts, &sp.mraw_nparts, ln); }
+        { Timed t(c, ST_COND_BWD_B); cond_bwd_b(sp.dev, cp, (double*)sp.esum_part.p, maxparts, &sp.esum_nparts, ln); }
+        { Timed t(c, ST_COND_BWD_A); cond_bwd_a(sa.dev, ca, (double*)sa.mraw_part.p, maxparts, &sa.mraw_nparts, ln); }
+        { Timed t(c, ST_COND_BWD_B); cond_bwd_b(sa.dev, ca, (double*)sa.esum_part.p, maxparts, &sa.esum_nparts, ln); }
     }
     const LayerRB* rbs[2] = {&rp, &ra};
+    Timed t_reduce(c, ST_REDUCE);
     for (int i = 0; i < 2; ++i) {
         LayerSlot* s = slots[i];
         const int64_t Mp = s->dev.Mp, E = 1 + 2 * s->dev.Dp;
@@ -495,6 +567,7 @@ int mgp_elbo_finish(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, 
     const LayerRB ra = layer_rb(rp.end, sa.dev.Mp, sa.dev.Dp, K);
     const double kl_coef = -1.0 / cfg->num_data;
     double* kl = (double*)c->kl.p;
+    Timed t_finish(c, ST_FINISH);
     finish_layer(sp.dev, reduce_buf + rp.S, reduce_buf + rp.mraw, reduce_buf + rp.esum, reduce_buf + RB_SUMV_PRED, kl_coef,
                  pg->Z, pg->q_mu, pg->q_sqrt, pg->variance, pg->lengthscales, kl, ln);
     finish_layer(sa.dev, reduce_buf + ra.S, reduce_buf + ra.mraw, reduce_buf + ra.esum, reduce_buf + RB_SUMV_ASSIGN, kl_coef,

@@ -100,8 +100,10 @@ def test_prior_kl_matches_oracle(hg):
         assert abs(float(layer.prior_kl()) - ref) <= 1e-12 * abs(ref)
 
 
-def _synthetic_case(N, D, M, K, S, seed, model="SMGP"):
-    """Config-#4-style synthetic workload at an oracle-sized N."""
+def _synthetic_case(N, D, M, K, S, seed, model="SMGP", ls_assign=1.1):
+    """Config-#4-style synthetic workload at an oracle-sized N.  SURVEY asks for cond(Kuu) <~ 1e4 so
+    that 1e-9 is above the conditioning noise floor; its assign lengthscale 1.5 on a unit grid gives cond 4e6, so
+    the strict cases use 1.1 (cond 1.3e4) and the 1.5 case is tested with a conditioning-scaled tolerance."""
     rng = np.random.default_rng(seed)
     side = int(round(math.sqrt(M)))
     if D == 2 and side * side == M:
@@ -109,7 +111,7 @@ def _synthetic_case(N, D, M, K, S, seed, model="SMGP"):
         grid = np.stack(np.meshgrid(gx, gx, indexing="ij"), -1).reshape(-1, 2)
         Zp, Za = grid + rng.uniform(-0.2, 0.2, grid.shape), grid + rng.uniform(-0.2, 0.2, grid.shape)
         X = rng.uniform(0, side, (N, D))
-        lsp, lsa = np.array([1.0, 1.0]), np.array([1.5, 1.5])
+        lsp, lsa = np.array([1.0, 1.0]), np.array([ls_assign, ls_assign])
     else:
         X = rng.standard_normal((N, D))
         pool = rng.standard_normal((2 * M, D))
@@ -145,6 +147,26 @@ def test_oracle_sized_synthetic_vs_oracle(N, D, M, K, S, hg):
     for k, r in rg.items():
         mine = grads[k].cpu().numpy().reshape(r.shape)
         assert relerr(mine, r) <= RTOL, (k, relerr(mine, r))
+
+
+def test_ill_conditioned_kuu_stays_within_the_conditioning_noise_floor(hg):
+    """SURVEY.md §8(d)'s literal config-#4 assign kernel (lengthscale 1.5 on a unit grid): cond(Kuu) = 3e6.  One-ulp
+    perturbations of Z move the ORACLE's own assign gradients by 6e-9 (measured), so 1e-9 is below the
+    noise floor here; the bar is 100 * eps * cond(Kuu) instead, and 1e-9 for everything on the well-conditioned side."""
+    from oracle import svgp_mixture as O
+    N, D, M, K, S = 3000, 2, 256, 4, 16
+    case, X, Y, z, u = _synthetic_case(N, D, M, K, S, seed=N, ls_assign=1.5)
+    cond = float(np.linalg.cond(O.kuu(O.layer_from_numpy(case["assign"])).numpy()))
+    tol_assign = max(RTOL, 100 * np.finfo(np.float64).eps * cond)
+    model = hg.build_model(case)
+    elbo, grads = model.elbo_and_grads(X, Y, noise=(z, u))
+    ref, rg = O.elbo_and_grads(case["model"], case["lik"], O.layer_from_numpy(case["pred"]), O.layer_from_numpy(case["assign"]),
+                               O.as_t(case["lik_var"]), None, X, Y, z, u, case["num_data"])
+    assert abs(float(elbo) - ref) <= RTOL * abs(ref)
+    for k, r in rg.items():
+        mine = grads[k].cpu().numpy().reshape(r.shape)
+        tol = tol_assign if k.startswith("assign.") else RTOL
+        assert relerr(mine, r) <= tol, (k, relerr(mine, r), cond)
 
 
 def test_chunking_and_sharding_invariance(hg):

@@ -1,0 +1,113 @@
+"""CPU: host-side logic of the package — the C-ABI library loads and exports every symbol include/mgp.h
+declares (no compute without a GPU), the product path fails loudly without CUDA, the bijector / fill-triangular
+maps match the TFP conventions, and the bench workload generator is deterministic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from modulatedgps_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "mgp.h")).read()
+    declared = set(re.findall(r"\b(mgp_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"mgp_layer", "mgp_layer_grad", "mgp_noise", "mgp_elbo_cfg", "mgp_ctx"}
+    assert len(declared) >= 18, declared
+    lib = ctypes.CDLL(built_lib)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/mgp.h but not exported by libmgp.so"
+    from modulatedgps_b200 import _lib
+    assert set(_lib.exported_symbols()) == declared, set(_lib.exported_symbols()) ^ declared
+    _lib.load_library()
+
+
+def test_ctypes_struct_layout_matches_header():
+    from modulatedgps_b200 import _lib
+    assert ctypes.sizeof(_lib.MgpLayer) == 4 * 4 + 5 * 8
+    assert ctypes.sizeof(_lib.MgpLayerGrad) == 5 * 8
+    assert ctypes.sizeof(_lib.MgpNoise) == 4 * 8
+    assert ctypes.sizeof(_lib.MgpElboCfg) == 4 * 4 + 2 * 8 + 8
+    assert _lib.MgpElboCfg.temperature.offset == 16 and _lib.MgpElboCfg.n_global.offset == 32
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(built_lib):
+    import modulatedgps_b200 as mg
+    from modulatedgps_b200 import _lib
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.get_context()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mg.SquaredExponential(1.0, 1.0)          # parameters live on the device
+    h = ctypes.c_void_p()
+    lib = _lib.load_library()
+    assert lib.mgp_ctx_create(0, None, ctypes.byref(h)) != 0 and not h.value
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "modulatedgps_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} mentions the oracle"
+
+
+def test_fill_triangular_matches_tfp_convention():
+    from modulatedgps_b200.parameter import fill_triangular_index
+    idx = fill_triangular_index(3)
+    x = np.array([1, 2, 3, 4, 5, 6])
+    mat = np.where(idx >= 0, x[np.maximum(idx, 0)], 0)
+    assert mat.tolist() == [[4, 0, 0], [6, 5, 0], [3, 2, 1]]        # TFP docstring example
+    from oracle.svgp_mixture import fill_triangular_index as oracle_idx
+    for m in (1, 2, 5, 25):
+        assert np.array_equal(fill_triangular_index(m), oracle_idx(m))
+
+
+def test_bijectors_roundtrip_and_chain_rule_on_cpu_tensors():
+    from modulatedgps_b200.parameter import FillTriangular, Softplus
+    sp = Softplus()
+    y = torch.tensor([1e-3, 0.1, 0.5, 3.0, 40.0], dtype=torch.float64)
+    x = sp.inverse(y)
+    assert torch.allclose(sp.forward(x), y, rtol=1e-14, atol=0)
+    xr = x.clone().requires_grad_(True)
+    sp.forward(xr).sum().backward()
+    assert torch.allclose(sp.grad_to_unconstrained(torch.ones_like(x), x), xr.grad, rtol=1e-14)
+    ft = FillTriangular()
+    v = torch.arange(1.0, 16.0, dtype=torch.float64).reshape(1, 15).repeat(2, 1)
+    Lm = ft.forward(v)
+    assert Lm.shape == (2, 5, 5) and torch.equal(torch.triu(Lm, 1), torch.zeros_like(Lm))
+    assert torch.equal(ft.inverse(Lm), v)
+    g = torch.randn(2, 5, 5, dtype=torch.float64)
+    vr = v.clone().requires_grad_(True)
+    (ft.forward(vr) * g).sum().backward()
+    assert torch.equal(ft.grad_to_unconstrained(g, v), vr.grad)
+
+
+def test_gauss_hermite_header_matches_numpy():
+    src = open(os.path.join(ROOT, "modulatedgps_b200", "csrc", "gh20.h")).read()
+    nums = [float(t) for t in re.findall(r"-?\d+\.\d+(?:e-?\d+)?", src.split("GH20_X[20]")[1])]
+    x, w = np.polynomial.hermite.hermgauss(20)
+    assert np.array_equal(np.array(nums[:20]), x) and np.array_equal(np.array(nums[20:40]), w)
+
+
+def test_bench_workload_is_deterministic_and_well_conditioned():
+    import bench
+    c1, X1, Y1 = bench.make_workload(2048, seed=0)
+    c2, X2, Y2 = bench.make_workload(2048, seed=0)
+    assert np.array_equal(X1, X2) and np.array_equal(Y1, Y2) and np.array_equal(c1["pred"]["Z"], c2["pred"]["Z"])
+    assert X1.shape == (2048, 2) and c1["pred"]["Z"].shape == (256, 2) and c1["pred"]["q_sqrt"].shape == (4, 256, 256)
+    assert bench.flops_per_point() == 1_999_872
+    from oracle import svgp_mixture as O
+    for lname in ("pred", "assign"):
+        cond = np.linalg.cond(O.kuu(O.layer_from_numpy(c1[lname])).numpy())
+        assert cond < 1e7, (lname, cond)

@@ -24,10 +24,10 @@ struct Buf {
 
 struct LayerSlot {
     LayerDev dev{};
-    Buf inv_ls, Zs_rm, Zs_fm, zs2, Kuu, L, Linv, W_Linv, W_LinvT, Lq_rm, W_LqT, Q_rm, W_Q, W_mT, T1, T2, T3, Sfull, rowout;
-    Buf A, asq, fmean, fvar, mubar, vbar;   // chunk buffers
+    Buf inv_ls, Zs_rm, Zs_fm, zs2, Kuu, L, Linv, W_Linv, W_LinvT, Lq_rm, W_LqT, Q_rm, W_Lq, W_m, W_mT, T1, T2, T3, Sfull, rowout;
+    Buf A, Bk, asq, fmean, fvar, mubar, vbar;   // chunk buffers
     Buf syrk_part, mraw_part, esum_part;    // per-CTA partial sums
-    int nsplit = 0, mraw_nparts = 0, esum_nparts = 0;
+    int nsplit = 0, esum_nparts = 0;
 };
 
 }  // namespace
@@ -172,17 +172,18 @@ int setup_layer(mgp_ctx* c, LayerSlot& s, const mgp_layer* l, bool need_bwd) {
     d.Lq_rm = (double*)s.Lq_rm.p; d.W_LqT = (double*)s.W_LqT.p; d.W_mT = (double*)s.W_mT.p;
     if (need_bwd) {
         TRY(ensure(c, s.Q_rm, K * mm));
-        TRY(ensure(c, s.W_Q, Mp * (K * Mp + KP) * 8));
+        TRY(ensure(c, s.W_Lq, K * mm));
+        TRY(ensure(c, s.W_m, Mp * KP * 8));
         TRY(ensure(c, s.T1, K * mm));
         TRY(ensure(c, s.T2, mm));
         TRY(ensure(c, s.T3, mm));
         TRY(ensure(c, s.Sfull, K * mm));
         TRY(ensure(c, s.rowout, Mp * (2 * Dp + 1) * 8));
-        d.Q_rm = (double*)s.Q_rm.p; d.W_Q = (double*)s.W_Q.p; d.T1 = (double*)s.T1.p; d.T2 = (double*)s.T2.p;
+        d.Q_rm = (double*)s.Q_rm.p; d.W_Lq = (double*)s.W_Lq.p; d.W_m = (double*)s.W_m.p; d.T1 = (double*)s.T1.p; d.T2 = (double*)s.T2.p;
         d.T3 = (double*)s.T3.p; d.Sfull = (double*)s.Sfull.p; d.rowout = (double*)s.rowout.p;
     } else {
         // forward-only paths still use T1 as scratch of nothing; keep pointers null-safe
-        d.Q_rm = d.W_Q = d.T1 = d.T2 = d.T3 = d.Sfull = d.rowout = nullptr;
+        d.Q_rm = d.W_Lq = d.W_m = d.T1 = d.T2 = d.T3 = d.Sfull = d.rowout = nullptr;
     }
     return MGP_OK;
 }
@@ -194,6 +195,7 @@ int ensure_chunk(mgp_ctx* c, LayerSlot& s, int64_t ldn, bool need_bwd) {
     TRY(ensure(c, s.fmean, (size_t)ldn * K * 8, true));
     TRY(ensure(c, s.fvar, (size_t)ldn * K * 8, true));
     if (need_bwd) {
+        TRY(ensure(c, s.Bk, K * Mp * (size_t)ldn * 8, true));
         TRY(ensure(c, s.mubar, (size_t)ldn * K * 8, true));
         TRY(ensure(c, s.vbar, (size_t)ldn * K * 8, true));
     }
@@ -203,7 +205,7 @@ int ensure_chunk(mgp_ctx* c, LayerSlot& s, int64_t ldn, bool need_bwd) {
 ChunkBuffers chunk_of(const LayerSlot& s, const double* X, int64_t n, int64_t ldn) {
     ChunkBuffers cb;
     cb.n = n; cb.ldn = ldn; cb.X = X;
-    cb.A = (double*)s.A.p; cb.asq = (double*)s.asq.p; cb.fmean = (double*)s.fmean.p; cb.fvar = (double*)s.fvar.p;
+    cb.A = (double*)s.A.p; cb.Bk = nullptr; cb.asq = (double*)s.asq.p; cb.fmean = (double*)s.fmean.p; cb.fvar = (double*)s.fvar.p;
     cb.mubar = (double*)s.mubar.p; cb.vbar = (double*)s.vbar.p;
     return cb;
 }
@@ -217,14 +219,14 @@ struct Timed {   // RAII stage bracket
 };
 
 // points per chunk so that the materialised A of `nlayers` layers fits the budget
-int64_t pick_chunk(mgp_ctx* c, int64_t N, int Mp_max, int nlayers) {
+int64_t pick_chunk(mgp_ctx* c, int64_t N, int Mp_max, int nlayers, int kcopies) {
     int64_t cap = c->chunk_cap;
     if (cap <= 0) {
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         double budget = fmin(0.4 * (double)c->total_mem, 0.7 * (double)free_b);
-        for (int i = 0; i < 2; ++i) budget += (double)c->slot[i].A.cap;   // what we already hold counts as available
-        cap = (int64_t)(budget / ((double)nlayers * (Mp_max + 6 * MGP_MAX_K) * 8.0));
+        for (int i = 0; i < 2; ++i) budget += (double)c->slot[i].A.cap + (double)c->slot[i].Bk.cap;   // what we already hold counts as available
+        cap = (int64_t)(budget / ((double)nlayers * ((1.0 + kcopies) * Mp_max + 6 * MGP_MAX_K) * 8.0));
         if (cap < 4096) cap = 4096;
     }
     cap = cap / 64 * 64;
@@ -264,7 +266,7 @@ int check_cfg(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, const 
 int run_predict_f(mgp_ctx* c, LayerSlot& s, const double* X, int64_t N, double* fmean, double* fvar) {
     const Launch ln = launch_of(c);
     const int K = s.dev.K, D = s.dev.D;
-    const int64_t Nc = pick_chunk(c, N, s.dev.Mp, 1);
+    const int64_t Nc = pick_chunk(c, N, s.dev.Mp, 1, 0);
     const int64_t ldn = round_up64(Nc, 64);
     TRY(ensure_chunk(c, s, ldn, false));
     for (int64_t c0 = 0; c0 < N; c0 += Nc) {
@@ -312,7 +314,7 @@ void mgp_ctx_destroy(mgp_ctx* c) {
     auto rel = [](Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; };
     for (auto& s : c->slot) {
         Buf* all[] = {&s.inv_ls, &s.Zs_rm, &s.Zs_fm, &s.zs2, &s.Kuu, &s.L, &s.Linv, &s.W_Linv, &s.W_LinvT, &s.Lq_rm,
-                      &s.W_LqT, &s.Q_rm, &s.W_Q, &s.W_mT, &s.T1, &s.T2, &s.T3, &s.Sfull, &s.rowout, &s.A, &s.asq,
+                      &s.W_LqT, &s.Q_rm, &s.W_Lq, &s.W_m, &s.W_mT, &s.T1, &s.T2, &s.T3, &s.Sfull, &s.rowout, &s.A, &s.Bk, &s.asq,
                       &s.fmean, &s.fvar, &s.mubar, &s.vbar, &s.syrk_part, &s.mraw_part, &s.esum_part};
         for (Buf* b : all) rel(*b);
     }
@@ -479,7 +481,7 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
     if (N_local == 0) return MGP_OK;   // an empty shard contributes zeros
 
     const int Mp_max = sp.dev.Mp > sa.dev.Mp ? sp.dev.Mp : sa.dev.Mp;
-    const int64_t Nc = pick_chunk(c, N_local, Mp_max, 2);
+    const int64_t Nc = pick_chunk(c, N_local, Mp_max, 2, K);
     const int64_t ldn = round_up64(Nc, 64);
     TRY(ensure_chunk(c, sp, ldn, true));
     TRY(ensure_chunk(c, sa, ldn, true));
@@ -489,12 +491,12 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
         const size_t Mp = s->dev.Mp, E = 1 + 2 * s->dev.Dp;
         s->nsplit = syrk_num_splits(s->dev.Mp, K, ln);
         TRY(ensure(c, s->syrk_part, (size_t)s->nsplit * K * Mp * Mp * 8));
-        TRY(ensure(c, s->mraw_part, (size_t)maxparts * Mp * KP * 8));
+        TRY(ensure(c, s->mraw_part, (size_t)s->nsplit * Mp * KP * 8));
         TRY(ensure(c, s->esum_part, (size_t)maxparts * Mp * E * 8));
         CUDA_TRY(c, cudaMemsetAsync(s->syrk_part.p, 0, (size_t)s->nsplit * K * Mp * Mp * 8, c->stream));
-        CUDA_TRY(c, cudaMemsetAsync(s->mraw_part.p, 0, (size_t)maxparts * Mp * KP * 8, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(s->mraw_part.p, 0, (size_t)s->nsplit * Mp * KP * 8, c->stream));
         CUDA_TRY(c, cudaMemsetAsync(s->esum_part.p, 0, (size_t)maxparts * Mp * E * 8, c->stream));
-        s->mraw_nparts = s->esum_nparts = 0;
+        s->esum_nparts = 0;
     }
     const int nblocks_max = mc_num_blocks(ldn);
     TRY(ensure(c, c->mc_part, (size_t)nblocks_max * MC_NPART * 8));
@@ -503,6 +505,8 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
         const int64_t n = (N_local - c0 < Nc) ? N_local - c0 : Nc;
         const int64_t ldc = round_up64(n, 64);   // padded extent of THIS chunk (<= ldn); leading dimension stays ldn
         ChunkBuffers cp = chunk_of(sp, X + c0 * D, n, ldn), ca = chunk_of(sa, X + c0 * D, n, ldn);
+        cp.Bk = (double*)sp.Bk.p;
+        ca.Bk = (double*)sa.Bk.p;
         { Timed t(c, ST_COND_FWD_A); cond_fwd_a(sp.dev, cp, ln); }
         { Timed t(c, ST_COND_FWD_B); cond_fwd_b(sp.dev, cp, ln); }
         { Timed t(c, ST_COND_FWD_A); cond_fwd_a(sa.dev, ca, ln); }
@@ -522,11 +526,11 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
             mc_pass(m, (double*)c->mc_part.p, ln);
             mc_fold((double*)c->mc_part.p, mc_num_blocks(ldc), reduce_buf, ln);
         }
-        { Timed t(c, ST_SYRK); syrk_accumulate(sp.dev, cp, (double*)sp.syrk_part.p, sp.nsplit, ln); }
-        { Timed t(c, ST_SYRK); syrk_accumulate(sa.dev, ca, (double*)sa.syrk_part.p, sa.nsplit, ln); }
-        { Timed t(c, ST_COND_BWD_A); cond_bwd_a(sp.dev, cp, (double*)sp.mraw_part.p, maxparts, &sp.mraw_nparts, ln); }
+        { Timed t(c, ST_SYRK); syrk_accumulate(sp.dev, cp, (double*)sp.syrk_part.p, (double*)sp.mraw_part.p, sp.nsplit, ln); }
+        { Timed t(c, ST_SYRK); syrk_accumulate(sa.dev, ca, (double*)sa.syrk_part.p, (double*)sa.mraw_part.p, sa.nsplit, ln); }
+        { Timed t(c, ST_COND_BWD_A); cond_bwd_a(sp.dev, cp, ln); }
         { Timed t(c, ST_COND_BWD_B); cond_bwd_b(sp.dev, cp, (double*)sp.esum_part.p, maxparts, &sp.esum_nparts, ln); }
-        { Timed t(c, ST_COND_BWD_A); cond_bwd_a(sa.dev, ca, (double*)sa.mraw_part.p, maxparts, &sa.mraw_nparts, ln); }
+        { Timed t(c, ST_COND_BWD_A); cond_bwd_a(sa.dev, ca, ln); }
         { Timed t(c, ST_COND_BWD_B); cond_bwd_b(sa.dev, ca, (double*)sa.esum_part.p, maxparts, &sa.esum_nparts, ln); }
     }
     const LayerRB* rbs[2] = {&rp, &ra};
@@ -536,7 +540,7 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
         const int64_t Mp = s->dev.Mp, E = 1 + 2 * s->dev.Dp;
         reduce_partials(reduce_buf + rbs[i]->S, (const double*)s->syrk_part.p, (int64_t)K * Mp * Mp, s->nsplit,
                         (int64_t)K * Mp * Mp, false, ln);
-        reduce_partials(reduce_buf + rbs[i]->mraw, (const double*)s->mraw_part.p, Mp * KP, s->mraw_nparts, Mp * KP, false, ln);
+        reduce_partials(reduce_buf + rbs[i]->mraw, (const double*)s->mraw_part.p, Mp * KP, s->nsplit, Mp * KP, false, ln);
         reduce_partials(reduce_buf + rbs[i]->esum, (const double*)s->esum_part.p, Mp * E, s->esum_nparts, Mp * E, false, ln);
     }
     CUDA_TRY(c, cudaGetLastError());

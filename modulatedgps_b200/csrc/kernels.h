@@ -39,6 +39,7 @@ struct ChunkBuffers {
     int64_t ldn;      // padded length (multiple of 64): leading dimension of the [Mp, ldn] arrays
     const double* X;  // [n, D] this chunk's rows
     double* A;        // [Mp, ldn]  A = L^-1 Kuf  (overwritten by Abar in the backward)
+    double* Bk;       // [K, Mp, ldn] B_k = Lq_k^T A, kept for the backward (null on forward-only paths)
     double* asq;      // [ldn]      |a_n|^2
     double* fmean;    // [ldn, K]
     double* fvar;     // [ldn, K]
@@ -49,9 +50,8 @@ struct ChunkBuffers {
 void cond_fwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln);
 // fmean = A^T q_mu, fvar = variance - |a|^2 + |Lq_k^T a|^2
 void cond_fwd_b(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln);
-// Abar = sum_k Q_k A diag(vbar_k) + q_mu mubar^T (in place over cb.A); mraw partial += A mubar
-void cond_bwd_a(const LayerDev& ly, const ChunkBuffers& cb, double* mraw_part, int nparts_cap, int* nparts,
-                const Launch& ln);
+// Abar = sum_k Lq_k (2 B_k diag(vbar_k)) + q_mu mubar^T - 2 A diag(sum_k vbar_k)   (in place over cb.A)
+void cond_bwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln);
 // Kuf_bar = L^-T Abar; E = Kuf_bar .* Kuf; esum partial += E [1, xs, xs^2]
 void cond_bwd_b(const LayerDev& ly, const ChunkBuffers& cb, double* esum_part, int nparts_cap, int* nparts,
                 const Launch& ln);
@@ -59,7 +59,9 @@ int stream_max_parts(const Launch& ln);
 
 // ---- syrk.cu : S_k += A diag(vbar_k) A^T ----------------------------------------------------------------
 // part: [nsplit, K, Mp, Mp]; each CTA accumulates into its own slot (deterministic); lower 64x64 tiles only.
-void syrk_accumulate(const LayerDev& ly, const ChunkBuffers& cb, double* part, int nsplit, const Launch& ln);
+// mraw_part: [nsplit, Mp, KP] += A mubar (computed by the J == 0 tile column, which sees every row of A).
+void syrk_accumulate(const LayerDev& ly, const ChunkBuffers& cb, double* part, double* mraw_part, int nsplit,
+                     const Launch& ln);
 int syrk_num_splits(int Mp, int K, const Launch& ln);
 
 // ---- mc_pass.cu : fused Monte-Carlo likelihood pass, forward + adjoints ------------------------------

@@ -25,7 +25,8 @@ struct LayerDev {
     double* Lq_rm;    // [K, Mp, Mp] rm  tril(q_sqrt), zero padded
     double* W_LqT;    // [K][Mp, Mp] fm  Lq_k^T          (upper)
     double* Q_rm;     // [K, Mp, Mp] rm  2 (Lq_k Lq_k^T - I)
-    double* W_Q;      // [Mp, K*Mp + KP] fm  [Q_0 | ... | Q_{K-1} | q_mu (KP cols)]
+    double* W_Lq;     // [K][Mp, Mp] fm  Lq_k            (lower)
+    double* W_m;      // [Mp, KP]   fm   q_mu padded to KP columns
     double* W_mT;     // [16, Mp]   fm   row k = q_mu[:, k] (k < K), 0 otherwise
     // backward accumulators / scratch
     double* T1;       // [K, Mp, Mp] rm scratch

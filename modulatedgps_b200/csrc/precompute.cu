@@ -270,10 +270,8 @@ void precompute_layer(const LayerDev& ly, bool need_bwd, int* d_status, const La
         gemm_small(Mp, Mp, Mp, 1.0, ly.Lq_rm, Mp, mm, false, ly.Lq_rm, Mp, mm, true, 0.0, ly.T1, Mp, mm, K, ln);
         q_finish_kernel<<<(unsigned)((K * mm + 255) / 256), 256, 0, ln.stream>>>(ly);
         ln.tick();
-        const int Ctot = K * Mp + KP;
-        for (int k = 0; k < K; ++k)
-            pack_fm(ly.W_Q, Mp, Mp, k * Mp, Ctot, ly.Q_rm + (int64_t)k * mm, Mp, Mp, Mp, false, 1, 0, 0, ln);
-        pack_fm(ly.W_Q, Mp, KP, K * Mp, Ctot, ly.q_mu, K, ly.M, K, false, 1, 0, 0, ln);
+        pack_fm(ly.W_Lq, Mp, Mp, 0, Mp, ly.Lq_rm, Mp, Mp, Mp, false, K, mm, mm, ln);
+        pack_fm(ly.W_m, Mp, KP, 0, KP, ly.q_mu, K, ly.M, K, false, 1, 0, 0, ln);
     }
 }
 

@@ -9,7 +9,7 @@
 //
 //   cond_fwd_a : T = Kuf tile (r^2 contraction on DMMA + exp)   A = L^-1 T            -> A, |a_n|^2
 //   cond_fwd_b : T = A tile        B_k = Lq_k^T T (norms only), mean = q_mu^T T       -> fmean, fvar
-//   cond_bwd_a : T = A tile        Abar = sum_k Q_k T diag(vbar_k) + q_mu mubar^T     -> Abar (over A), A mubar
+//   cond_bwd_a : T = B_k tiles     Abar = sum_k Lq_k T_k diag(2 vbar_k) + q_mu mubar^T - 2 A diag(sum vbar)  -> Abar (over A)
 //   cond_bwd_b : T = Abar tile     Kuf_bar = L^-T T ; E = Kuf_bar .* Kuf              -> sums E [1, xs, xs^2]
 //
 // Reference arithmetic replaced: gpflow SquaredExponential.K + base_conditional as called from
@@ -25,7 +25,6 @@ namespace mgp {
 
 constexpr int SK_WARPS = 8;
 constexpr int SK_THREADS = SK_WARPS * 32;
-constexpr int MUB_STR = 12;  // [n][k] staging stride of mubar (conflict-free B-fragment loads)
 
 __host__ __device__ inline int xs_stride(int Dp) { return ((Dp - 4 + 15) / 16) * 16 + 4; }
 
@@ -262,10 +261,14 @@ __global__ void __launch_bounds__(SK_THREADS) cond_fwd_b_kernel(LayerDev ly, Chu
                 double acc[2][NF][2];
                 zero_acc<NF>(acc);
                 wgemm_block<NT, false>(Wk, C4, 2 * b, b * 4, C4, T, acc, sc_dummy, lane);   // upper triangular
+                double* Bk = cb.Bk ? cb.Bk + (size_t)k * Mp * cb.ldn : nullptr;
 #pragma unroll
                 for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
                     for (int nf = 0; nf < NF; ++nf) {
+                        if (Bk)   // kept for the backward: Abar needs Lq_k (2 B_k diag(vbar_k))
+                            *reinterpret_cast<double2*>(Bk + (size_t)(b * 16 + mf * 8 + g) * cb.ldn + n0 + nf * 8 + 2 * t) =
+                                make_double2(acc[mf][nf][0], acc[mf][nf][1]);
                         colsq[nf][0] += acc[mf][nf][0] * acc[mf][nf][0];
                         colsq[nf][1] += acc[mf][nf][1] * acc[mf][nf][1];
                     }
@@ -303,76 +306,70 @@ __global__ void __launch_bounds__(SK_THREADS) cond_fwd_b_kernel(LayerDev ly, Chu
 }
 
 // ==================================================================================================
-// cond_bwd_a
+// cond_bwd_a  (triangular route)
+//   Abar = sum_k Lq_k * (B_k diag(2 vbar_k))  +  q_mu * mubar^T  -  2 A diag(sum_k vbar_k)
+// from fvar = variance - |a|^2 + sum |b_k|^2, b_k = Lq_k^T a, fmean = a^T q_mu.  The right operand changes with k
+// (B_k tiles, re-staged K times per point tile), so each warp keeps the accumulators of ALL its row blocks
+// (NBW of them) in registers across the k loop.  Executed flops = algorithmic K M^2 (x17/16).
 // ==================================================================================================
-template <int NT>
-__global__ void __launch_bounds__(SK_THREADS) cond_bwd_a_kernel(LayerDev ly, ChunkBuffers cb, int ntiles,
-                                                                double* mraw_part) {
+template <int NT, int NBW>
+__global__ void __launch_bounds__(SK_THREADS) cond_bwd_a_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
     constexpr int NF = NT / 8, STR = NT + 4;
     extern __shared__ __align__(16) double smem[];
     const int Mp = ly.Mp, K = ly.K;
     double* T = smem;
     double* mubT = T + (size_t)Mp * STR;  // [KP][STR]   mubar^T (right operand of the q_mu segment)
-    double* mubN = mubT + KP * STR;       // [NT][MUB_STR] mubar (right operand of A mubar)
-    double* vb = mubN + NT * MUB_STR;     // [KP][NT]    vbar^T
+    double* vb = mubT + KP * STR;         // [KP + 1][NT]  vbar^T, last row = sum_k vbar_k
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    const int nb16 = Mp / 16, C4 = Mp / 4, C4tot = (K * Mp + KP) / 4;
-    double* my_part = mraw_part + (size_t)blockIdx.x * Mp * KP;
+    const int nb16 = Mp / 16, C4 = Mp / 4;
     const double sc_dummy[NF] = {};
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t n0 = (int64_t)tile * NT;
-        load_tile_async<NT>(T, cb.A, Mp, cb.ldn, n0);
         for (int idx = threadIdx.x; idx < NT * KP; idx += SK_THREADS) {
             const int n = idx / KP, k = idx % KP;
-            const double mv = k < K ? cb.mubar[(size_t)(n0 + n) * K + k] : 0.0;
-            const double vv = k < K ? cb.vbar[(size_t)(n0 + n) * K + k] : 0.0;
-            mubT[k * STR + n] = mv;
-            mubN[n * MUB_STR + k] = mv;
-            vb[k * NT + n] = vv;
+            mubT[k * STR + n] = k < K ? cb.mubar[(size_t)(n0 + n) * K + k] : 0.0;
+            vb[k * NT + n] = k < K ? cb.vbar[(size_t)(n0 + n) * K + k] : 0.0;
         }
-        cp_async_wait<0>();
-        __syncthreads();
-        for (int round = 0; round * SK_WARPS < nb16; ++round) {
-            const int b = snake_block(round, warp, nb16);
+        for (int n = threadIdx.x; n < NT; n += SK_THREADS) {
+            double s = 0.0;
+            for (int k = 0; k < K; ++k) s += cb.vbar[(size_t)(n0 + n) * K + k];
+            vb[KP * NT + n] = s;
+        }
+        double acc[NBW][2][NF][2];
+#pragma unroll
+        for (int r = 0; r < NBW; ++r) zero_acc<NF>(acc[r]);
+        for (int k = 0; k < K; ++k) {
+            __syncthreads();   // everyone is done with the previous right operand (and the staging above is visible)
+            load_tile_async<NT>(T, cb.Bk + (size_t)k * Mp * cb.ldn, Mp, cb.ldn, n0);
+            cp_async_wait<0>();
+            __syncthreads();
+            double sc[NF];
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf) sc[nf] = 2.0 * vb[k * NT + nf * 8 + g];
+            const double* Wk = ly.W_Lq + (size_t)k * Mp * Mp;
+#pragma unroll
+            for (int r = 0; r < NBW; ++r) {
+                const int b = snake_block(r, warp, nb16);
+                if (b >= 0) wgemm_block<NT, true>(Wk, C4, 2 * b, 0, (b + 1) * 4, T, acc[r], sc, lane);   // lower triangular
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NBW; ++r) {
+            const int b = snake_block(r, warp, nb16);
             if (b < 0) continue;
-            // (1) q_mu gradient partial: (A mubar)[rows, k] over this tile's points
-            {
-                double am[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-                for (int ks = 0; ks < NT / 4; ++ks) {
-                    const double bb = mubN[(ks * 4 + t) * MUB_STR + g];
-#pragma unroll
-                    for (int mf = 0; mf < 2; ++mf)
-                        dmma(am[mf], T[(size_t)(b * 16 + mf * 8 + g) * STR + ks * 4 + t], bb);
-                }
-#pragma unroll
-                for (int mf = 0; mf < 2; ++mf) {
-                    double* p = my_part + (size_t)(b * 16 + mf * 8 + g) * KP + 2 * t;
-                    p[0] += am[mf][0];
-                    p[1] += am[mf][1];
-                }
-            }
-            // (2) Abar rows
-            double acc[2][NF][2];
-            zero_acc<NF>(acc);
-            for (int k = 0; k < K; ++k) {
-                double sc[NF];
-#pragma unroll
-                for (int nf = 0; nf < NF; ++nf) sc[nf] = vb[k * NT + nf * 8 + g];
-                wgemm_block<NT, true>(ly.W_Q + (size_t)k * C4 * 32, C4tot, 2 * b, 0, C4, T, acc, sc, lane);
-            }
-            wgemm_block<NT, false>(ly.W_Q + (size_t)K * C4 * 32, C4tot, 2 * b, 0, KP / 4, mubT, acc, sc_dummy, lane);
+            wgemm_block<NT, false>(ly.W_m, KP / 4, 2 * b, 0, KP / 4, mubT, acc[r], sc_dummy, lane);
 #pragma unroll
             for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
                 for (int nf = 0; nf < NF; ++nf) {
-                    const size_t row = (size_t)(b * 16 + mf * 8 + g);
-                    *reinterpret_cast<double2*>(cb.A + row * cb.ldn + n0 + nf * 8 + 2 * t) =
-                        make_double2(acc[mf][nf][0], acc[mf][nf][1]);
+                    double2* p = reinterpret_cast<double2*>(cb.A + (size_t)(b * 16 + mf * 8 + g) * cb.ldn + n0 + nf * 8 + 2 * t);
+                    const double2 av = *p;
+                    const double v0 = vb[KP * NT + nf * 8 + 2 * t], v1 = vb[KP * NT + nf * 8 + 2 * t + 1];
+                    *p = make_double2(acc[r][mf][nf][0] - 2.0 * v0 * av.x, acc[r][mf][nf][1] - 2.0 * v1 * av.y);
                 }
         }
-        __syncthreads();
+        __syncthreads();   // mubT / vb are re-staged by the next tile
     }
 }
 
@@ -495,18 +492,25 @@ void cond_fwd_b(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
     if (nt == 32) launch(cond_fwd_b_kernel<32>, 32); else launch(cond_fwd_b_kernel<16>, 16);
 }
 
-void cond_bwd_a(const LayerDev& ly, const ChunkBuffers& cb, double* mraw_part, int nparts_cap, int* nparts,
-                const Launch& ln) {
-    const int nt = pick_nt(ly.Mp, (size_t)(KP * 36 + 32 * MUB_STR + KP * 32) * 8);
+void cond_bwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
+    const int nt = pick_nt(ly.Mp, (size_t)(KP * 36 + (KP + 1) * 32) * 8);
+    const int nbw = (ly.Mp / 16 + SK_WARPS - 1) / SK_WARPS;   // 16-row blocks per warp
     auto launch = [&](auto kernel, int NT) {
-        const size_t smem = ((size_t)ly.Mp * (NT + 4) + KP * (NT + 4) + NT * MUB_STR + KP * NT) * sizeof(double);
+        const size_t smem = ((size_t)ly.Mp * (NT + 4) + KP * (NT + 4) + (KP + 1) * NT) * sizeof(double);
         const int ntiles = (int)((cb.n + NT - 1) / NT);
-        const int grid = persistent_grid(kernel, smem, ntiles, nparts_cap, ln);
-        kernel<<<grid, SK_THREADS, smem, ln.stream>>>(ly, cb, ntiles, mraw_part);
+        const int grid = persistent_grid(kernel, smem, ntiles, 0, ln);
+        kernel<<<grid, SK_THREADS, smem, ln.stream>>>(ly, cb, ntiles);
         ln.tick();
-        if (grid > *nparts) *nparts = grid;
     };
-    if (nt == 32) launch(cond_bwd_a_kernel<32>, 32); else launch(cond_bwd_a_kernel<16>, 16);
+    if (nt == 32 && nbw <= 4) {   // accumulators of all row blocks live in registers: NBW*2*NF*2 doubles per lane
+        if (nbw <= 1) launch(cond_bwd_a_kernel<32, 1>, 32);
+        else if (nbw <= 2) launch(cond_bwd_a_kernel<32, 2>, 32);
+        else launch(cond_bwd_a_kernel<32, 4>, 32);
+    } else {
+        if (nbw <= 4) launch(cond_bwd_a_kernel<16, 4>, 16);
+        else if (nbw <= 8) launch(cond_bwd_a_kernel<16, 8>, 16);
+        else launch(cond_bwd_a_kernel<16, 11>, 16);
+    }
 }
 
 void cond_bwd_b(const LayerDev& ly, const ChunkBuffers& cb, double* esum_part, int nparts_cap, int* nparts,

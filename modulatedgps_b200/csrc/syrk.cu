@@ -17,10 +17,11 @@ namespace mgp {
 constexpr int SY_KC = 32;           // points per stage
 constexpr int SY_STR = SY_KC + 4;   // == 4 mod 16: conflict-free fragment loads
 constexpr int SY_THREADS = 256;
-constexpr int SY_STAGE = 2 * 64 * SY_STR + 4 * SY_KC;  // doubles per stage: AI, AJ, weights[4][KC]
+constexpr int SY_MUB = 12;          // [n][k] stride of the mubar slab (conflict-free B-fragment loads)
+constexpr int SY_STAGE = 2 * 64 * SY_STR + 4 * SY_KC + SY_KC * SY_MUB;  // doubles per stage: AI, AJ, weights[4][KC], mubar[KC][12]
 
-__device__ __forceinline__ void syrk_load_stage(double* st, const double* A, const double* vbar, int Mp, int K,
-                                                int64_t ldn, int I, int J, int kbase, int64_t p0) {
+__device__ __forceinline__ void syrk_load_stage(double* st, const double* A, const double* vbar, const double* mubar,
+                                                int Mp, int K, int64_t ldn, int I, int J, int kbase, int64_t p0) {
     double* AI = st;
     double* AJ = st + 64 * SY_STR;
     double* wt = st + 2 * 64 * SY_STR;
@@ -35,11 +36,19 @@ __device__ __forceinline__ void syrk_load_stage(double* st, const double* A, con
         const int k = kbase + kl;
         wt[kl * SY_KC + n] = k < K ? vbar[(size_t)(p0 + n) * K + k] : 0.0;
     }
+    if (mubar != nullptr) {
+        double* mb = st + 2 * 64 * SY_STR + 4 * SY_KC;
+        for (int idx = threadIdx.x; idx < SY_KC * KP; idx += SY_THREADS) {
+            const int n = idx / KP, k = idx % KP;
+            mb[n * SY_MUB + k] = k < K ? mubar[(size_t)(p0 + n) * K + k] : 0.0;
+        }
+    }
     cp_async_commit();
 }
 
-__global__ void __launch_bounds__(SY_THREADS, 1) syrk_kernel(const double* A, const double* vbar, double* part, int Mp,
-                                                             int K, int64_t ldn, int64_t n, int64_t per_split) {
+__global__ void __launch_bounds__(SY_THREADS, 1) syrk_kernel(const double* A, const double* vbar, const double* mubar,
+                                                             double* part, double* mraw_part, int Mp, int K, int64_t ldn,
+                                                             int64_t n, int64_t per_split) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     // tile pair (I >= J) from blockIdx.x
@@ -55,6 +64,10 @@ __global__ void __launch_bounds__(SY_THREADS, 1) syrk_kernel(const double* A, co
     if (pend > nround) pend = nround;
     if (pbeg >= pend) return;
     const int nstage = (int)((pend - pbeg) / SY_KC);
+    // the J == 0 tile column of component group 0 sees every row block of A exactly once: it also forms A mubar
+    const bool do_mraw = (J == 0 && blockIdx.z == 0);
+    const double* mub_src = do_mraw ? mubar : nullptr;
+    double am[2] = {0.0, 0.0};
 
     for (int idx = threadIdx.x; idx < 2 * SY_STAGE; idx += SY_THREADS) smem[idx] = 0.0;   // rows >= Mp stay zero
     __syncthreads();
@@ -65,11 +78,12 @@ __global__ void __launch_bounds__(SY_THREADS, 1) syrk_kernel(const double* A, co
 #pragma unroll
         for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-    syrk_load_stage(smem, A, vbar, Mp, K, ldn, I, J, kbase, pbeg);
+    syrk_load_stage(smem, A, vbar, mub_src, Mp, K, ldn, I, J, kbase, pbeg);
     for (int s = 0; s < nstage; ++s) {
         double* cur = smem + (s & 1) * SY_STAGE;
         if (s + 1 < nstage) {
-            syrk_load_stage(smem + ((s + 1) & 1) * SY_STAGE, A, vbar, Mp, K, ldn, I, J, kbase, pbeg + (int64_t)(s + 1) * SY_KC);
+            syrk_load_stage(smem + ((s + 1) & 1) * SY_STAGE, A, vbar, mub_src, Mp, K, ldn, I, J, kbase,
+                            pbeg + (int64_t)(s + 1) * SY_KC);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
@@ -93,7 +107,21 @@ __global__ void __launch_bounds__(SY_THREADS, 1) syrk_kernel(const double* A, co
                     for (int ni = 0; ni < 8; ++ni) dmma(acc[mi][ni], a[mi], b[ni]);
             }
         }
+        if (do_mraw) {   // warp w: rows I*64 + 8w .. +8 ; columns = components
+            const double* AIw = cur + (warp * 8 + g) * SY_STR + t;
+            const double* mb = cur + 2 * 64 * SY_STR + 4 * SY_KC + t * SY_MUB + g;
+#pragma unroll
+            for (int ks = 0; ks < SY_KC / 4; ++ks) dmma(am, AIw[ks * 4], mb[ks * 4 * SY_MUB]);
+        }
         __syncthreads();
+    }
+    if (do_mraw) {
+        const int row = I * 64 + warp * 8 + g;
+        if (row < Mp) {
+            double* p = mraw_part + ((size_t)split * Mp + row) * KP + 2 * t;
+            p[0] += am[0];
+            p[1] += am[1];
+        }
     }
     if (k < K) {
         double* P = part + ((size_t)split * K + k) * Mp * Mp;
@@ -117,7 +145,8 @@ int syrk_num_splits(int Mp, int K, const Launch& ln) {
     return ns < 1 ? 1 : ns;
 }
 
-void syrk_accumulate(const LayerDev& ly, const ChunkBuffers& cb, double* part, int nsplit, const Launch& ln) {
+void syrk_accumulate(const LayerDev& ly, const ChunkBuffers& cb, double* part, double* mraw_part, int nsplit,
+                     const Launch& ln) {
     const int nb = (ly.Mp + 63) / 64, npairs = nb * (nb + 1) / 2, kgroups = (ly.K + 3) / 4;
     const int64_t nchunks = (cb.n + SY_KC - 1) / SY_KC;
     int ns = nsplit;
@@ -126,7 +155,8 @@ void syrk_accumulate(const LayerDev& ly, const ChunkBuffers& cb, double* part, i
     const size_t smem = 2 * SY_STAGE * sizeof(double);
     cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(npairs, ns, kgroups);
-    syrk_kernel<<<grid, SY_THREADS, smem, ln.stream>>>(cb.A, cb.vbar, part, ly.Mp, ly.K, cb.ldn, cb.n, per_split);
+    syrk_kernel<<<grid, SY_THREADS, smem, ln.stream>>>(cb.A, cb.vbar, cb.mubar, part, mraw_part, ly.Mp, ly.K, cb.ldn, cb.n,
+                                                       per_split);
     ln.tick();
 }
 

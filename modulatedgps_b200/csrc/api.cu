@@ -75,6 +75,8 @@ struct mgp_ctx {
     StageTimer timer;
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;          // the assign layer's replicated work runs here, concurrently with the pred layer's
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int num_sms = 0;
     size_t total_mem = 0;
     int64_t launches = 0;
@@ -157,7 +159,7 @@ int setup_layer(mgp_ctx* c, LayerSlot& s, const mgp_layer* l, bool need_bwd) {
     TRY(ensure(c, s.inv_ls, Dp * 8));
     TRY(ensure(c, s.Zs_rm, Mp * Dp * 8));
     TRY(ensure(c, s.Zs_fm, Mp * Dp * 8));
-    TRY(ensure(c, s.zs2, Mp * 8));
+    TRY(ensure(c, s.zs2, (2 * Mp + 16) * 8));   // [Mp] |Zs_i|^2 + [Mp..] small scratch (KL partials)
     TRY(ensure(c, s.Kuu, mm));
     TRY(ensure(c, s.L, mm));
     TRY(ensure(c, s.Linv, mm));
@@ -211,6 +213,17 @@ ChunkBuffers chunk_of(const LayerSlot& s, const double* X, int64_t n, int64_t ld
 }
 
 Launch launch_of(mgp_ctx* c) { return Launch{c->stream, &c->launches, c->num_sms}; }
+
+// fork the side stream off the main one / join it back (the two layers' replicated O(M^3) work is independent)
+Launch fork_side(mgp_ctx* c) {
+    cudaEventRecord(c->ev_fork, c->stream);
+    cudaStreamWaitEvent(c->side, c->ev_fork, 0);
+    return Launch{c->side, &c->launches, c->num_sms};
+}
+void join_side(mgp_ctx* c) {
+    cudaEventRecord(c->ev_join, c->side);
+    cudaStreamWaitEvent(c->stream, c->ev_join, 0);
+}
 
 struct Timed {   // RAII stage bracket
     mgp_ctx* c;
@@ -299,6 +312,12 @@ int mgp_ctx_create(int device, void* cuda_stream, mgp_ctx** out) {
     c->stream = (cudaStream_t)cuda_stream;
     c->num_sms = prop.multiProcessorCount;
     c->total_mem = prop.totalGlobalMem;
+    if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        delete c;
+        return MGP_ERR_CUDA;
+    }
     if (ensure(c, c->kl, 64) != MGP_OK || ensure(c, c->status, 64, true) != MGP_OK) {
         delete c;
         return MGP_ERR_NOMEM;
@@ -319,6 +338,9 @@ void mgp_ctx_destroy(mgp_ctx* c) {
         for (Buf* b : all) rel(*b);
     }
     rel(c->mc_part); rel(c->scratch_rb); rel(c->kl); rel(c->status);
+    if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
 }
 
@@ -474,8 +496,10 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
 
     {
         Timed t(c, ST_PRECOMPUTE);
+        const Launch ls = fork_side(c);
         precompute_layer(sp.dev, true, (int*)c->status.p, ln);
-        precompute_layer(sa.dev, true, (int*)c->status.p, ln);
+        precompute_layer(sa.dev, true, (int*)c->status.p, ls);
+        join_side(c);
     }
     c->pre_valid = true;
     if (N_local == 0) return MGP_OK;   // an empty shard contributes zeros
@@ -562,8 +586,10 @@ int mgp_elbo_finish(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, 
     TRY(setup_layer(c, sp, pred, true));
     TRY(setup_layer(c, sa, assign, true));
     if (!c->pre_valid) {
+        const Launch ls = fork_side(c);
         precompute_layer(sp.dev, true, (int*)c->status.p, ln);
-        precompute_layer(sa.dev, true, (int*)c->status.p, ln);
+        precompute_layer(sa.dev, true, (int*)c->status.p, ls);
+        join_side(c);
         c->pre_valid = true;
     }
     const int K = pred->K;
@@ -572,10 +598,12 @@ int mgp_elbo_finish(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, 
     const double kl_coef = -1.0 / cfg->num_data;
     double* kl = (double*)c->kl.p;
     Timed t_finish(c, ST_FINISH);
+    const Launch ls = fork_side(c);
     finish_layer(sp.dev, reduce_buf + rp.S, reduce_buf + rp.mraw, reduce_buf + rp.esum, reduce_buf + RB_SUMV_PRED, kl_coef,
                  pg->Z, pg->q_mu, pg->q_sqrt, pg->variance, pg->lengthscales, kl, ln);
     finish_layer(sa.dev, reduce_buf + ra.S, reduce_buf + ra.mraw, reduce_buf + ra.esum, reduce_buf + RB_SUMV_ASSIGN, kl_coef,
-                 ag->Z, ag->q_mu, ag->q_sqrt, ag->variance, ag->lengthscales, kl + 1, ln);
+                 ag->Z, ag->q_mu, ag->q_sqrt, ag->variance, ag->lengthscales, kl + 1, ls);
+    join_side(c);
     elbo_finalize_kernel<<<1, 32, 0, c->stream>>>(reduce_buf, kl, cfg->num_data, K, elbo,
                                                   cfg->lik == MGP_LIK_GAUSSIAN ? lik_var_grad : nullptr,
                                                   cfg->model == MGP_MODEL_SMGP_MODIFIED ? assign_lik_var_grad : nullptr);

@@ -24,7 +24,7 @@ struct LayerDev {
     double* W_LinvT;  // [Mp, Mp]   fm   L^-T            (upper)
     double* Lq_rm;    // [K, Mp, Mp] rm  tril(q_sqrt), zero padded
     double* W_LqT;    // [K][Mp, Mp] fm  Lq_k^T          (upper)
-    double* Q_rm;     // [K, Mp, Mp] rm  2 (Lq_k Lq_k^T - I)
+    double* Q_rm;     // [Mp, K*Mp]  rm  [Q_0 | ... | Q_{K-1}],  Q_k = 2 (Lq_k Lq_k^T - I)
     double* W_Lq;     // [K][Mp, Mp] fm  Lq_k            (lower)
     double* W_m;      // [Mp, KP]   fm   q_mu padded to KP columns
     double* W_mT;     // [16, Mp]   fm   row k = q_mu[:, k] (k < K), 0 otherwise

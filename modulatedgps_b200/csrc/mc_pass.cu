@@ -8,7 +8,8 @@
 //   SMGP.E_log_p_Y / SMGPModified.E_log_p_Y      models.py:63-67 / 112-123  (logsumexp over samples)
 // and TF's reverse pass through them.  The pass is HBM-bound: per point it reads 4K conditionals + y and (parity
 // mode) 2 S K noise values, coalesced and vectorised by the [.., N, K] layouts, and writes 4K adjoints.
-// Two sweeps over the samples (online logsumexp, then adjoints) avoid any per-thread [S] storage.
+// One sweep over the samples: the softmax-over-samples weighted adjoints are accumulated online (running maximum +
+// rescale), so no per-thread [S] storage and no recomputation of the noise / Gumbel-softmax is needed.
 #include <float.h>
 #include <math.h>
 
@@ -139,6 +140,43 @@ __device__ __forceinline__ void sample_weights(const double (&mu_a)[K], const do
     for (int k = 0; k < K; ++k) W[k] = exp((x[k] - mx) - lse);
 }
 
+// softmax-over-samples weighted accumulators of one logsumexp term, online (flash-attention style)
+template <int K>
+struct OnlineTerm {
+    double m = -DBL_MAX, s = 0.0;
+    double mu[K], v[K], e[K];
+    __device__ __forceinline__ OnlineTerm() {
+#pragma unroll
+        for (int k = 0; k < K; ++k) mu[k] = v[k] = e[k] = 0.0;
+    }
+    // one sample: weights W, per-component values c (t = sum_k W_k c_k), the normal draw z, sd = sqrt(var + jitter)
+    __device__ __forceinline__ void add(const double (&W)[K], const double (&c)[K], const double (&z)[K],
+                                        const double (&sd)[K], double temperature) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) t += W[k] * c[k];
+        double w;
+        if (t > m) {
+            const double scale = exp(m - t);   // exp(-huge) = 0 on the first sample
+            s = s * scale + 1.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) { mu[k] *= scale; v[k] *= scale; e[k] *= scale; }
+            m = t;
+            w = 1.0;
+        } else {
+            w = exp(t - m);
+            s += w;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double xb = w * (c[k] * W[k] - W[k] * t) / temperature;   // d/d logits_k (up to 1/(s n))
+            mu[k] += xb;
+            v[k] += xb * z[k] * (0.5 / sd[k]);
+            e[k] += w * W[k];
+        }
+    }
+};
+
 template <int K>
 __device__ __forceinline__ void load_noise(const McArgs& a, int64_t i, int s, double (&z)[K], double (&u)[K]) {
     if (a.z != nullptr) {
@@ -197,63 +235,40 @@ __global__ void __launch_bounds__(MC_THREADS) mc_pass_kernel(McArgs a, double* b
                 eA[k] = -HALF_LOG_2PI - 0.5 * log(s) - 0.5 * (r * r + var_a[k]) / s;
             }
         }
-        // sweep 1: online logsumexp over the samples
-        double my = -DBL_MAX, sy = 0.0, mA = -DBL_MAX, sA = 0.0;
+        // ONE sweep over the samples.  The adjoints are softmax_s(t_s)-weighted sums, so they are accumulated with a
+        // running maximum and rescaled whenever it moves (online softmax), then normalised by the final sum:
+        //   w_s = exp(t_s - lse) / n_global ;  d/dW_k = w_s c_k ;  through exp(log_softmax(x)):
+        //   xbar_k = Wbar_k W_k - W_k sum_j Wbar_j W_j = w_s (c_k W_k - W_k t_s)          (c = e or eA, t = sum_k W_k c_k)
+        OnlineTerm<K> ty_acc, tA_acc;
         for (int s = 0; s < a.S; ++s) {
             double z[K], u[K], W[K];
             load_noise<K>(a, i, s, z, u);
             sample_weights<K>(mu_a, sd_a, z, u, a.temperature, W);
-            double ty = 0.0, tA = 0.0;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                ty += W[k] * e[k];
-                if (MODEL == 1) tA += W[k] * eA[k];
-            }
-            if (ty > my) { sy = sy * exp(my - ty) + 1.0; my = ty; } else { sy += exp(ty - my); }
-            if (MODEL == 1) {
-                if (tA > mA) { sA = sA * exp(mA - tA) + 1.0; mA = tA; } else { sA += exp(tA - mA); }
-            }
+            ty_acc.add(W, e, z, sd_a, a.temperature);
+            if (MODEL == 1) tA_acc.add(W, eA, z, sd_a, a.temperature);
         }
         const double logS = log((double)a.S);
-        const double lse_y = log(sy) + my;
+        const double lse_y = log(ty_acc.s) + ty_acc.m;
         double lse_A = 0.0;
-        if (MODEL == 1) lse_A = log(sA) + mA;
+        if (MODEL == 1) lse_A = log(tA_acc.s) + tA_acc.m;
         // SMGP: logsumexp_s(t) - log S ; Modified: logsumexp_s(tA - log S) + logsumexp_s(ty - log S)
         data = (MODEL == 0) ? (lse_y - logS) : ((lse_A - logS) + (lse_y - logS));
         data *= a.inv_n_global;
-
-        // sweep 2: adjoints
         double mub_a[K], vb_a[K], ebar[K], eAbar[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) mub_a[k] = vb_a[k] = ebar[k] = eAbar[k] = 0.0;
-        for (int s = 0; s < a.S; ++s) {
-            double z[K], u[K], W[K];
-            load_noise<K>(a, i, s, z, u);
-            sample_weights<K>(mu_a, sd_a, z, u, a.temperature, W);
-            double ty = 0.0, tA = 0.0;
+        {
+            const double ny = a.inv_n_global / ty_acc.s;
+            const double nA = (MODEL == 1) ? a.inv_n_global / tA_acc.s : 0.0;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                ty += W[k] * e[k];
-                if (MODEL == 1) tA += W[k] * eA[k];
-            }
-            const double wy = exp(ty - lse_y) * a.inv_n_global;
-            const double wA = (MODEL == 1) ? exp(tA - lse_A) * a.inv_n_global : 0.0;
-            // d/dW_k, then through exp(log_softmax(x)) :  xbar_k = Wbar_k W_k - W_k sum_j Wbar_j W_j
-            double gW[K], dot = 0.0;
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                double wb = wy * e[k];
-                if (MODEL == 1) wb += wA * eA[k];
-                gW[k] = wb * W[k];
-                dot += gW[k];
-                ebar[k] += wy * W[k];
-                if (MODEL == 1) eAbar[k] += wA * W[k];
-            }
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const double xb = (gW[k] - W[k] * dot) / a.temperature;   // d/d logits_k
-                mub_a[k] += xb;
-                vb_a[k] += xb * z[k] * (0.5 / sd_a[k]);
+                mub_a[k] = ty_acc.mu[k] * ny;
+                vb_a[k] = ty_acc.v[k] * ny;
+                ebar[k] = ty_acc.e[k] * ny;
+                eAbar[k] = 0.0;
+                if (MODEL == 1) {
+                    mub_a[k] += tA_acc.mu[k] * nA;
+                    vb_a[k] += tA_acc.v[k] * nA;
+                    eAbar[k] = tA_acc.e[k] * nA;
+                }
             }
         }
         // through the likelihood terms

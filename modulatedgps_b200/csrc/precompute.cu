@@ -239,14 +239,15 @@ __global__ void lq_clean_kernel(LayerDev ly) {
     ly.Lq_rm[idx] = (i < M && j <= i) ? ly.q_sqrt[((size_t)k * M + i) * M + j] : 0.0;
 }
 
-// Q_rm[k] = 2 (T1[k] - I_M)
+// Q_rm = [Q_0 | ... | Q_{K-1}]  ([Mp, K*Mp] row-major),  Q_k = 2 (T1[k] - I_M)
 __global__ void q_finish_kernel(LayerDev ly) {
-    const int Mp = ly.Mp, M = ly.M;
+    const int Mp = ly.Mp, M = ly.M, K = ly.K;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)ly.K * Mp * Mp) return;
+    if (idx >= (int64_t)K * Mp * Mp) return;
+    const int k = (int)(idx / ((int64_t)Mp * Mp));
     const int rem = (int)(idx % ((int64_t)Mp * Mp));
     const int i = rem / Mp, j = rem % Mp;
-    ly.Q_rm[idx] = 2.0 * (ly.T1[idx] - ((i == j && i < M) ? 1.0 : 0.0));
+    ly.Q_rm[(size_t)i * K * Mp + (size_t)k * Mp + j] = 2.0 * (ly.T1[idx] - ((i == j && i < M) ? 1.0 : 0.0));
 }
 
 void precompute_layer(const LayerDev& ly, bool need_bwd, int* d_status, const Launch& ln) {
@@ -399,26 +400,45 @@ __global__ void __launch_bounds__(128) kuu_bwd_kernel(LayerDev ly, const double*
 }
 
 // gauss_kl (whitened): 0.5 [ sum q_mu^2 - M K - sum log diag(Lq)^2 + sum Lq^2 ]
-__global__ void __launch_bounds__(256) kl_kernel(LayerDev ly, double* kl_out) {
+// stage 1: one CTA per component k sums its Lq_k terms (block K: the q_mu term); stage 2: fixed-order total.
+__global__ void __launch_bounds__(256) kl_part_kernel(LayerDev ly, double* part) {
     __shared__ double red[32];
-    const int M = ly.M, Mp = ly.Mp, K = ly.K;
+    const int M = ly.M, Mp = ly.Mp, K = ly.K, k = blockIdx.x;
     double s = 0.0;
-    for (int idx = threadIdx.x; idx < M * K; idx += blockDim.x) {
-        const double v = ly.q_mu[idx];
-        s += v * v;
-    }
-    for (int64_t idx = threadIdx.x; idx < (int64_t)K * M * M; idx += blockDim.x) {
-        const int k = (int)(idx / ((int64_t)M * M));
-        const int rem = (int)(idx % ((int64_t)M * M));
-        const int i = rem / M, j = rem % M;
-        if (j <= i) {
-            const double v = ly.Lq_rm[((size_t)k * Mp + i) * Mp + j];
+    if (k < K) {
+        const double* Lq = ly.Lq_rm + (size_t)k * Mp * Mp;
+        for (int idx = threadIdx.x; idx < M * Mp; idx += blockDim.x) {
+            const int i = idx / Mp, j = idx - i * Mp;
+            if (j <= i) {
+                const double v = Lq[idx];
+                s += v * v;
+                if (i == j) s -= log(v * v);
+            }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < M * K; idx += blockDim.x) {
+            const double v = ly.q_mu[idx];
             s += v * v;
-            if (i == j) s -= log(v * v);
         }
     }
     s = block_sum(s, red);
-    if (threadIdx.x == 0) kl_out[0] = 0.5 * (s - (double)M * (double)K);
+    if (threadIdx.x == 0) part[k] = s;
+}
+
+__global__ void kl_total_kernel(LayerDev ly, const double* part, double* kl_out) {
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k <= ly.K; ++k) s += part[k];
+        kl_out[0] = 0.5 * (s - (double)ly.M * (double)ly.K);
+    }
+}
+
+static void kl_launch(const LayerDev& ly, double* kl_out, const Launch& ln) {
+    // rowout doubles as the [K + 1] partial buffer when it exists; Kuu's padding rows are free otherwise
+    double* part = ly.zs2 + ly.Mp;   // zs2 is allocated with 2 * Mp doubles (api.cu); second half = scratch
+    kl_part_kernel<<<ly.K + 1, 256, 0, ln.stream>>>(ly, part);
+    kl_total_kernel<<<1, 32, 0, ln.stream>>>(ly, part, kl_out);
+    ln.tick(2);
 }
 
 // final assembly of dZ, dlengthscales, dvariance from the streamed sums (esum), the Kuu path (rowout) and Knn
@@ -458,8 +478,8 @@ __global__ void __launch_bounds__(256) assemble_kernel(LayerDev ly, const double
 void prior_kl_layer(const LayerDev& ly, double* kl_out, const Launch& ln) {
     const int64_t mm = (int64_t)ly.Mp * ly.Mp;
     lq_clean_kernel<<<(unsigned)((ly.K * mm + 255) / 256), 256, 0, ln.stream>>>(ly);
-    kl_kernel<<<1, 256, 0, ln.stream>>>(ly, kl_out);
-    ln.tick(2);
+    ln.tick();
+    kl_launch(ly, kl_out, ln);
 }
 
 void finish_layer(const LayerDev& ly, const double* S_lower, const double* mraw, const double* esum,
@@ -476,9 +496,7 @@ void finish_layer(const LayerDev& ly, const double* S_lower, const double* mraw,
     gqmu_kernel<<<(M * K + 255) / 256, 256, 0, ln.stream>>>(ly, mraw, kl_coef, gqmu);
     ln.tick(2);
     // T = tril( sum_k Q_k S_k + q_mu mraw^T )  ( = Abar A^T )
-    for (int k = 0; k < K; ++k)
-        gemm_small(Mp, Mp, Mp, 1.0, ly.Q_rm + k * mm, Mp, 0, false, ly.Sfull + k * mm, Mp, 0, false, k ? 1.0 : 0.0,
-                   ly.T2, Mp, 0, 1, ln);
+    gemm_small(Mp, Mp, K * Mp, 1.0, ly.Q_rm, K * Mp, 0, false, ly.Sfull, Mp, 0, false, 0.0, ly.T2, Mp, 0, 1, ln);
     t_finish_kernel<<<gmm, 256, 0, ln.stream>>>(ly, mraw);
     // Lbar = -tril(L^-T T)
     gemm_small(Mp, Mp, Mp, 1.0, ly.Linv, Mp, 0, true, ly.T2, Mp, 0, false, 0.0, ly.T3, Mp, 0, 1, ln);
@@ -492,8 +510,8 @@ void finish_layer(const LayerDev& ly, const double* S_lower, const double* mraw,
     // kernel backward on Kuu
     kuu_bwd_kernel<<<M, 128, 0, ln.stream>>>(ly, ly.T3, ly.rowout);
     assemble_kernel<<<1, 256, 0, ln.stream>>>(ly, esum, ly.rowout, sumv, gZ, gvar, gls);
-    kl_kernel<<<1, 256, 0, ln.stream>>>(ly, kl_out);
-    ln.tick(3);
+    ln.tick(2);
+    kl_launch(ly, kl_out, ln);
 }
 
 }  // namespace mgp

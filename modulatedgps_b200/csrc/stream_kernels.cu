@@ -106,6 +106,59 @@ __device__ __forceinline__ void zero_acc(double (&acc)[2][NF][2]) {
         for (int nf = 0; nf < NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
 }
 
+// number of 16-row blocks dealt to this warp (only the last snake round can be short)
+__device__ __forceinline__ int my_block_count(int warp, int nb16) {
+    const int R = (nb16 + SK_WARPS - 1) / SK_WARPS;
+    return R == 0 ? 0 : (snake_block(R - 1, warp, nb16) >= 0 ? R : R - 1);
+}
+
+// ---- cross-segment software pipelining of the left-operand fragments ------------------------------------------
+// A warp's work is a fixed sequence of segments (pass, 16-row block, k-range).  The first fragment group of the
+// NEXT segment is fetched while the last group of the current one is multiplied, so no L2 round trip is exposed at
+// block / pass / tile boundaries.
+struct Seg {
+    const double* w;   // fragment-major base of this pass's left operand (k4-block 0 of row-block 0)
+    int rb8;           // first 8-row block of the 16-row block
+    int kb0;           // first k4-block of the segment
+};
+struct WFrag {
+    double a0[4], a1[4];
+};
+__device__ __forceinline__ void wfrag_load(WFrag& f, const Seg& sg, int C4, int kb, int lane) {
+    const double* w0 = sg.w + ((size_t)sg.rb8 * C4 + kb) * 32 + lane;
+    const double* w1 = w0 + (size_t)C4 * 32;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        f.a0[j] = __ldg(w0 + j * 32);
+        f.a1[j] = __ldg(w1 + j * 32);
+    }
+}
+// acc += W[segment rows, kb0..kb1) * T ; (kb1 - kb0) must be a positive multiple of 4.  On entry `f` holds the
+// first group of `cur`; on exit it holds the first group of `nxt`.
+template <int NT>
+__device__ __forceinline__ void wgemm_seg(const Seg& cur, int kb1, int C4, const double* Tsm, double (&acc)[2][NT / 8][2],
+                                          int lane, WFrag& f, const Seg& nxt) {
+    constexpr int NF = NT / 8, STR = NT + 4;
+    const int g = lane >> 2, t = lane & 3;
+    const double* tb = Tsm + t * STR + g;
+    for (int kb = cur.kb0; kb < kb1; kb += 4) {
+        WFrag n;
+        if (kb + 4 < kb1) wfrag_load(n, cur, C4, kb + 4, lane);
+        else wfrag_load(n, nxt, C4, nxt.kb0, lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double* tr = tb + (size_t)(kb + j) * 4 * STR;
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf) {
+                const double b = tr[nf * 8];
+                dmma(acc[0][nf], f.a0[j], b);
+                dmma(acc[1][nf], f.a1[j], b);
+            }
+        }
+        f = n;
+    }
+}
+
 // Xs[n][d] = X[n0+n][d] / lengthscale_d (0 outside the chunk / padding); xs2[n] = |Xs_n|^2
 template <int NT>
 __device__ __forceinline__ void stage_x(const LayerDev& ly, const ChunkBuffers& cb, int64_t n0, double* Xs,
@@ -179,7 +232,10 @@ __global__ void __launch_bounds__(SK_THREADS) cond_fwd_a_kernel(LayerDev ly, Chu
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nb16 = Mp / 16, nb8 = Mp / 8, C4 = Mp / 4;
     const double variance = ly.variance[0];
-    const double sc_dummy[NF] = {};
+    const int nmy = my_block_count(warp, nb16);
+    auto seg_of = [&](int i) { const int b = snake_block(i, warp, nb16); return Seg{ly.W_Linv, 2 * b, 0}; };
+    WFrag wf;
+    if (nmy > 0) wfrag_load(wf, seg_of(0), C4, 0, lane);
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t n0 = (int64_t)tile * NT;
@@ -195,12 +251,11 @@ __global__ void __launch_bounds__(SK_THREADS) cond_fwd_a_kernel(LayerDev ly, Chu
         double colsq[NF][2];
 #pragma unroll
         for (int nf = 0; nf < NF; ++nf) colsq[nf][0] = colsq[nf][1] = 0.0;
-        for (int round = 0; round * SK_WARPS < nb16; ++round) {
-            const int b = snake_block(round, warp, nb16);
-            if (b < 0) continue;
+        for (int i = 0; i < nmy; ++i) {
+            const int b = snake_block(i, warp, nb16);
             double acc[2][NF][2];
             zero_acc<NF>(acc);
-            wgemm_block<NT, false>(ly.W_Linv, C4, 2 * b, 0, (b + 1) * 4, T, acc, sc_dummy, lane);   // lower triangular
+            wgemm_seg<NT>(seg_of(i), (b + 1) * 4, C4, T, acc, lane, wf, seg_of(i + 1 < nmy ? i + 1 : 0));   // lower triangular
 #pragma unroll
             for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
@@ -243,7 +298,16 @@ __global__ void __launch_bounds__(SK_THREADS) cond_fwd_b_kernel(LayerDev ly, Chu
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nb16 = Mp / 16, C4 = Mp / 4;
     const double variance = ly.variance[0];
-    const double sc_dummy[NF] = {};
+    const int nmy = my_block_count(warp, nb16);
+    const bool does_mean = (warp == SK_WARPS - 1);
+    const Seg mean_seg{ly.W_mT, 0, 0};
+    auto seg_of = [&](int k, int i) {
+        const int b = snake_block(i, warp, nb16);
+        return Seg{ly.W_LqT + (size_t)k * Mp * Mp, 2 * b, 4 * b};
+    };
+    auto first_seg = [&]() { return nmy > 0 ? seg_of(0, 0) : mean_seg; };
+    WFrag wf;
+    if (nmy > 0 || does_mean) { const Seg s0 = first_seg(); wfrag_load(wf, s0, C4, s0.kb0, lane); }
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t n0 = (int64_t)tile * NT;
@@ -254,13 +318,12 @@ __global__ void __launch_bounds__(SK_THREADS) cond_fwd_b_kernel(LayerDev ly, Chu
             double colsq[NF][2];
 #pragma unroll
             for (int nf = 0; nf < NF; ++nf) colsq[nf][0] = colsq[nf][1] = 0.0;
-            const double* Wk = ly.W_LqT + (size_t)k * Mp * Mp;
-            for (int round = 0; round * SK_WARPS < nb16; ++round) {
-                const int b = snake_block(round, warp, nb16);
-                if (b < 0) continue;
+            for (int i = 0; i < nmy; ++i) {
+                const int b = snake_block(i, warp, nb16);
                 double acc[2][NF][2];
                 zero_acc<NF>(acc);
-                wgemm_block<NT, false>(Wk, C4, 2 * b, b * 4, C4, T, acc, sc_dummy, lane);   // upper triangular
+                const Seg nxt = (i + 1 < nmy) ? seg_of(k, i + 1) : (k + 1 < K ? seg_of(k + 1, 0) : (does_mean ? mean_seg : seg_of(0, 0)));
+                wgemm_seg<NT>(seg_of(k, i), C4, C4, T, acc, lane, wf, nxt);   // upper triangular
                 double* Bk = cb.Bk ? cb.Bk + (size_t)k * Mp * cb.ldn : nullptr;
 #pragma unroll
                 for (int mf = 0; mf < 2; ++mf)
@@ -281,10 +344,10 @@ __global__ void __launch_bounds__(SK_THREADS) cond_fwd_b_kernel(LayerDev ly, Chu
                     if (g == 0) colpart[((size_t)warp * KP + k) * NT + nf * 8 + 2 * t + e] = s;
                 }
         }
-        if (warp == SK_WARPS - 1) {  // fmean^T [K x NT] = q_mu^T [K x Mp] * A tile
+        if (does_mean) {  // fmean^T [K x NT] = q_mu^T [K x Mp] * A tile
             double acc[2][NF][2];
             zero_acc<NF>(acc);
-            wgemm_block<NT, false>(ly.W_mT, C4, 0, 0, C4, T, acc, sc_dummy, lane);
+            wgemm_seg<NT>(mean_seg, C4, C4, T, acc, lane, wf, first_seg());
             if (g < K) {
 #pragma unroll
                 for (int nf = 0; nf < NF; ++nf)
@@ -317,59 +380,106 @@ __global__ void __launch_bounds__(SK_THREADS) cond_bwd_a_kernel(LayerDev ly, Chu
     constexpr int NF = NT / 8, STR = NT + 4;
     extern __shared__ __align__(16) double smem[];
     const int Mp = ly.Mp, K = ly.K;
-    double* T = smem;
-    double* mubT = T + (size_t)Mp * STR;  // [KP][STR]   mubar^T (right operand of the q_mu segment)
-    double* vb = mubT + KP * STR;         // [KP + 1][NT]  vbar^T, last row = sum_k vbar_k
+    // double-buffered right operand (B_k tiles) and per-tile adjoint slabs: the next (tile, k) operand streams in
+    // with cp.async while the current one is being multiplied
+    double* Tb = smem;                               // [2][Mp][STR]
+    double* mubTb = Tb + 2 * (size_t)Mp * STR;       // [2][KP][STR]  mubar^T (right operand of the q_mu segment)
+    double* vbb = mubTb + 2 * KP * STR;              // [2][KP][NT]   vbar^T
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nb16 = Mp / 16, C4 = Mp / 4;
     const double sc_dummy[NF] = {};
 
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t n0 = (int64_t)tile * NT;
-        for (int idx = threadIdx.x; idx < NT * KP; idx += SK_THREADS) {
-            const int n = idx / KP, k = idx % KP;
-            mubT[k * STR + n] = k < K ? cb.mubar[(size_t)(n0 + n) * K + k] : 0.0;
-            vb[k * NT + n] = k < K ? cb.vbar[(size_t)(n0 + n) * K + k] : 0.0;
-        }
-        for (int n = threadIdx.x; n < NT; n += SK_THREADS) {
-            double s = 0.0;
-            for (int k = 0; k < K; ++k) s += cb.vbar[(size_t)(n0 + n) * K + k];
-            vb[KP * NT + n] = s;
-        }
-        double acc[NBW][2][NF][2];
-#pragma unroll
-        for (int r = 0; r < NBW; ++r) zero_acc<NF>(acc[r]);
-        for (int k = 0; k < K; ++k) {
-            __syncthreads();   // everyone is done with the previous right operand (and the staging above is visible)
-            load_tile_async<NT>(T, cb.Bk + (size_t)k * Mp * cb.ldn, Mp, cb.ldn, n0);
-            cp_async_wait<0>();
-            __syncthreads();
-            double sc[NF];
-#pragma unroll
-            for (int nf = 0; nf < NF; ++nf) sc[nf] = 2.0 * vb[k * NT + nf * 8 + g];
-            const double* Wk = ly.W_Lq + (size_t)k * Mp * Mp;
-#pragma unroll
-            for (int r = 0; r < NBW; ++r) {
-                const int b = snake_block(r, warp, nb16);
-                if (b >= 0) wgemm_block<NT, true>(Wk, C4, 2 * b, 0, (b + 1) * 4, T, acc[r], sc, lane);   // lower triangular
+    for (int idx = threadIdx.x; idx < 2 * KP * STR + 2 * KP * NT; idx += SK_THREADS) mubTb[idx] = 0.0;   // k >= K rows stay 0
+    __syncthreads();
+    const int nmy = my_block_count(warp, nb16);
+    auto seg_of = [&](int k, int i) {
+        const int b = snake_block(i, warp, nb16);
+        return Seg{ly.W_Lq + (size_t)k * Mp * Mp, 2 * b, 0};
+    };
+    WFrag wf;
+    if (nmy > 0) wfrag_load(wf, seg_of(0, 0), C4, 0, lane);
+
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = my_tiles * K;
+    auto issue = [&](int j) {   // stage operand j = (tile iteration, component) into buffer j & 1
+        const int ti = j / K, k = j - ti * K;
+        const int64_t n0 = (int64_t)(blockIdx.x + ti * gridDim.x) * NT;
+        load_tile_async<NT>(Tb + (size_t)(j & 1) * Mp * STR, cb.Bk + (size_t)k * Mp * cb.ldn, Mp, cb.ldn, n0);
+        if (k == 0) {
+            double* mT = mubTb + (size_t)(ti & 1) * KP * STR;
+            double* vT = vbb + (size_t)(ti & 1) * KP * NT;
+            for (int idx = threadIdx.x; idx < NT * K; idx += SK_THREADS) {
+                const int n = idx / K, kk = idx - n * K;
+                cp_async8(mT + kk * STR + n, cb.mubar + (size_t)(n0 + n) * K + kk);
+                cp_async8(vT + kk * NT + n, cb.vbar + (size_t)(n0 + n) * K + kk);
             }
+            cp_async_commit();
+        }
+    };
+    if (total > 0) issue(0);
+    double acc[NBW][2][NF][2];
+    for (int j = 0; j < total; ++j) {
+        const int ti = j / K, k = j - ti * K;
+        const int64_t n0 = (int64_t)(blockIdx.x + ti * gridDim.x) * NT;
+        cp_async_wait<0>();    // operand j has landed ...
+        __syncthreads();       // ... for everyone, and every warp is done with operand j - 1
+        if (j + 1 < total) issue(j + 1);   // refill the buffer operand j - 1 used
+        const double* T = Tb + (size_t)(j & 1) * Mp * STR;
+        const double* mubT = mubTb + (size_t)(ti & 1) * KP * STR;
+        const double* vb = vbb + (size_t)(ti & 1) * KP * NT;
+        if (k == 0) {
+#pragma unroll
+            for (int r = 0; r < NBW; ++r) zero_acc<NF>(acc[r]);
+        }
+        // column weights 2 vbar_k of this lane's columns; applied once per (block, k) to the finished product
+        // Lq_k B_k instead of to every B fragment (keeps DMUL out of the DMMA loop)
+        double sc[NF][2];
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) {
+            sc[nf][0] = 2.0 * vb[k * NT + nf * 8 + 2 * t];
+            sc[nf][1] = 2.0 * vb[k * NT + nf * 8 + 2 * t + 1];
         }
 #pragma unroll
         for (int r = 0; r < NBW; ++r) {
+            if (r >= nmy) continue;
             const int b = snake_block(r, warp, nb16);
-            if (b < 0) continue;
-            wgemm_block<NT, false>(ly.W_m, KP / 4, 2 * b, 0, KP / 4, mubT, acc[r], sc_dummy, lane);
+            double ck[2][NF][2];
+            zero_acc<NF>(ck);
+            const Seg nxt = (r + 1 < nmy) ? seg_of(k, r + 1) : seg_of(k + 1 < K ? k + 1 : 0, 0);
+            wgemm_seg<NT>(seg_of(k, r), (b + 1) * 4, C4, T, ck, lane, wf, nxt);   // lower triangular
 #pragma unroll
             for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
                 for (int nf = 0; nf < NF; ++nf) {
-                    double2* p = reinterpret_cast<double2*>(cb.A + (size_t)(b * 16 + mf * 8 + g) * cb.ldn + n0 + nf * 8 + 2 * t);
-                    const double2 av = *p;
-                    const double v0 = vb[KP * NT + nf * 8 + 2 * t], v1 = vb[KP * NT + nf * 8 + 2 * t + 1];
-                    *p = make_double2(acc[r][mf][nf][0] - 2.0 * v0 * av.x, acc[r][mf][nf][1] - 2.0 * v1 * av.y);
+                    acc[r][mf][nf][0] = fma(ck[mf][nf][0], sc[nf][0], acc[r][mf][nf][0]);
+                    acc[r][mf][nf][1] = fma(ck[mf][nf][1], sc[nf][1], acc[r][mf][nf][1]);
                 }
         }
-        __syncthreads();   // mubT / vb are re-staged by the next tile
+        if (k == K - 1) {   // tile epilogue: + q_mu mubar^T - 2 A diag(sum_k vbar_k), in place over A
+            double vs[NF][2];
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf) {
+                vs[nf][0] = vs[nf][1] = 0.0;
+                for (int kk = 0; kk < K; ++kk) {
+                    vs[nf][0] += vb[kk * NT + nf * 8 + 2 * t];
+                    vs[nf][1] += vb[kk * NT + nf * 8 + 2 * t + 1];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < NBW; ++r) {
+                const int b = snake_block(r, warp, nb16);
+                if (b < 0) continue;
+                wgemm_block<NT, false>(ly.W_m, KP / 4, 2 * b, 0, KP / 4, mubT, acc[r], sc_dummy, lane);
+#pragma unroll
+                for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf) {
+                        double2* p = reinterpret_cast<double2*>(cb.A + (size_t)(b * 16 + mf * 8 + g) * cb.ldn + n0 + nf * 8 + 2 * t);
+                        const double2 av = *p;
+                        *p = make_double2(acc[r][mf][nf][0] - 2.0 * vs[nf][0] * av.x, acc[r][mf][nf][1] - 2.0 * vs[nf][1] * av.y);
+                    }
+            }
+        }
     }
 }
 
@@ -389,7 +499,10 @@ __global__ void __launch_bounds__(SK_THREADS) cond_bwd_b_kernel(LayerDev ly, Chu
     const int nb16 = Mp / 16, C4 = Mp / 4;
     const double variance = ly.variance[0];
     double* my_part = esum_part + (size_t)blockIdx.x * Mp * E;
-    const double sc_dummy[NF] = {};
+    const int nmy = my_block_count(warp, nb16);
+    auto seg_of = [&](int i) { const int b = snake_block(i, warp, nb16); return Seg{ly.W_LinvT, 2 * b, 4 * b}; };
+    WFrag wf;
+    if (nmy > 0) wfrag_load(wf, seg_of(0), C4, seg_of(0).kb0, lane);
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t n0 = (int64_t)tile * NT;
@@ -397,12 +510,11 @@ __global__ void __launch_bounds__(SK_THREADS) cond_bwd_b_kernel(LayerDev ly, Chu
         stage_x<NT>(ly, cb, n0, Xs, xs2);
         cp_async_wait<0>();
         __syncthreads();
-        for (int round = 0; round * SK_WARPS < nb16; ++round) {
-            const int b = snake_block(round, warp, nb16);
-            if (b < 0) continue;
+        for (int i = 0; i < nmy; ++i) {
+            const int b = snake_block(i, warp, nb16);
             double acc[2][NF][2];
             zero_acc<NF>(acc);
-            wgemm_block<NT, false>(ly.W_LinvT, C4, 2 * b, b * 4, C4, T, acc, sc_dummy, lane);   // upper triangular
+            wgemm_seg<NT>(seg_of(i), C4, C4, T, acc, lane, wf, seg_of(i + 1 < nmy ? i + 1 : 0));   // upper triangular
 #pragma unroll
             for (int mf = 0; mf < 2; ++mf) {
                 double kv[NF][2];
@@ -416,8 +528,10 @@ __global__ void __launch_bounds__(SK_THREADS) cond_bwd_b_kernel(LayerDev ly, Chu
                         e0 += acc[mf][nf][e];
                     }
                 double* p = my_part + (size_t)(b * 16 + mf * 8 + g) * E;
+                // fire-and-forget reductions: each address has exactly ONE writer (this lane, this CTA's private slot), so
+                // the accumulation order is fixed and the result deterministic; RED avoids the load-add-store round trip
                 e0 = sum_over_t(e0);
-                if (t == 0) p[0] += e0;
+                if (t == 0) atomicAdd(p, e0);
                 for (int d = 0; d < D; ++d) {
                     double e1 = 0.0, e2 = 0.0;
 #pragma unroll
@@ -432,8 +546,8 @@ __global__ void __launch_bounds__(SK_THREADS) cond_bwd_b_kernel(LayerDev ly, Chu
                     e1 = sum_over_t(e1);
                     e2 = sum_over_t(e2);
                     if (t == 0) {
-                        p[1 + d] += e1;
-                        p[1 + Dp + d] += e2;
+                        atomicAdd(p + 1 + d, e1);
+                        atomicAdd(p + 1 + Dp + d, e2);
                     }
                 }
             }
@@ -458,6 +572,7 @@ static int pick_nt(int Mp, size_t extra_bytes_nt32) {
 template <typename KernelT>
 static int persistent_grid(KernelT kernel, size_t smem, int ntiles, int cap, const Launch& ln) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, SK_THREADS, smem);
     if (occ < 1) occ = 1;
@@ -493,10 +608,13 @@ void cond_fwd_b(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
 }
 
 void cond_bwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
-    const int nt = pick_nt(ly.Mp, (size_t)(KP * 36 + (KP + 1) * 32) * 8);
+    // double-buffered operand: two [Mp x (NT+4)] tiles must fit
+    int nt = 0;
+    if (2 * ((size_t)ly.Mp * 36 + KP * 36 + KP * 32) * 8 <= 227 * 1024) nt = 32;
+    else if (2 * ((size_t)ly.Mp * 20 + KP * 20 + KP * 16) * 8 <= 227 * 1024) nt = 16;
     const int nbw = (ly.Mp / 16 + SK_WARPS - 1) / SK_WARPS;   // 16-row blocks per warp
     auto launch = [&](auto kernel, int NT) {
-        const size_t smem = ((size_t)ly.Mp * (NT + 4) + KP * (NT + 4) + (KP + 1) * NT) * sizeof(double);
+        const size_t smem = 2 * ((size_t)ly.Mp * (NT + 4) + KP * (NT + 4) + KP * NT) * sizeof(double);
         const int ntiles = (int)((cb.n + NT - 1) / NT);
         const int grid = persistent_grid(kernel, smem, ntiles, 0, ln);
         kernel<<<grid, SK_THREADS, smem, ln.stream>>>(ly, cb, ntiles);

@@ -17,6 +17,7 @@ namespace mgp {
 constexpr int SY_KC = 32;           // points per stage
 constexpr int SY_STR = SY_KC + 4;   // == 4 mod 16: conflict-free fragment loads
 constexpr int SY_THREADS = 256;
+constexpr int SY_NSTAGE = 3;
 constexpr int SY_MUB = 12;          // [n][k] stride of the mubar slab (conflict-free B-fragment loads)
 constexpr int SY_STAGE = 2 * 64 * SY_STR + 4 * SY_KC + SY_KC * SY_MUB;  // doubles per stage: AI, AJ, weights[4][KC], mubar[KC][12]
 
@@ -31,16 +32,17 @@ __device__ __forceinline__ void syrk_load_stage(double* st, const double* A, con
         if (ri < Mp) cp_async16(AI + row * SY_STR + 2 * c2, A + (size_t)ri * ldn + p0 + 2 * c2);
         if (I != J && rj < Mp) cp_async16(AJ + row * SY_STR + 2 * c2, A + (size_t)rj * ldn + p0 + 2 * c2);
     }
+    // weights / mubar slabs: 8-byte async copies (entries for k >= K are never written and stay zero)
     for (int idx = threadIdx.x; idx < 4 * SY_KC; idx += SY_THREADS) {
         const int kl = idx / SY_KC, n = idx % SY_KC;
         const int k = kbase + kl;
-        wt[kl * SY_KC + n] = k < K ? vbar[(size_t)(p0 + n) * K + k] : 0.0;
+        if (k < K) cp_async8(wt + kl * SY_KC + n, vbar + (size_t)(p0 + n) * K + k);
     }
     if (mubar != nullptr) {
         double* mb = st + 2 * 64 * SY_STR + 4 * SY_KC;
-        for (int idx = threadIdx.x; idx < SY_KC * KP; idx += SY_THREADS) {
-            const int n = idx / KP, k = idx % KP;
-            mb[n * SY_MUB + k] = k < K ? mubar[(size_t)(p0 + n) * K + k] : 0.0;
+        for (int idx = threadIdx.x; idx < SY_KC * K; idx += SY_THREADS) {
+            const int n = idx / K, k = idx - n * K;
+            cp_async8(mb + n * SY_MUB + k, mubar + (size_t)(p0 + n) * K + k);
         }
     }
     cp_async_commit();
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) syrk_kernel(const double* A, co
     const double* mub_src = do_mraw ? mubar : nullptr;
     double am[2] = {0.0, 0.0};
 
-    for (int idx = threadIdx.x; idx < 2 * SY_STAGE; idx += SY_THREADS) smem[idx] = 0.0;   // rows >= Mp stay zero
+    for (int idx = threadIdx.x; idx < SY_NSTAGE * SY_STAGE; idx += SY_THREADS) smem[idx] = 0.0;   // rows >= Mp stay zero
     __syncthreads();
 
     double acc[4][8][2];
@@ -78,17 +80,22 @@ __global__ void __launch_bounds__(SY_THREADS, 1) syrk_kernel(const double* A, co
 #pragma unroll
         for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
 
-    syrk_load_stage(smem, A, vbar, mub_src, Mp, K, ldn, I, J, kbase, pbeg);
+    // SY_NSTAGE-deep cp.async ring, ONE barrier per stage: after the barrier of iteration s every warp has finished
+    // multiplying stage s-1, so its buffer can be refilled (with stage s + SY_NSTAGE - 1) right away.
+#pragma unroll
+    for (int p = 0; p < SY_NSTAGE - 1; ++p) {
+        if (p < nstage) syrk_load_stage(smem + p * SY_STAGE, A, vbar, mub_src, Mp, K, ldn, I, J, kbase, pbeg + (int64_t)p * SY_KC);
+        else cp_async_commit();
+    }
     for (int s = 0; s < nstage; ++s) {
-        double* cur = smem + (s & 1) * SY_STAGE;
-        if (s + 1 < nstage) {
-            syrk_load_stage(smem + ((s + 1) & 1) * SY_STAGE, A, vbar, mub_src, Mp, K, ldn, I, J, kbase,
-                            pbeg + (int64_t)(s + 1) * SY_KC);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+        double* cur = smem + (s % SY_NSTAGE) * SY_STAGE;
+        cp_async_wait<SY_NSTAGE - 2>();   // stage s has landed (only the newest SY_NSTAGE-2 groups may be pending)
         __syncthreads();
+        if (s + SY_NSTAGE - 1 < nstage)
+            syrk_load_stage(smem + ((s + SY_NSTAGE - 1) % SY_NSTAGE) * SY_STAGE, A, vbar, mub_src, Mp, K, ldn, I, J, kbase,
+                            pbeg + (int64_t)(s + SY_NSTAGE - 1) * SY_KC);
+        else
+            cp_async_commit();   // empty group keeps the wait count uniform
         if (k < K) {
             const double* AI = cur + (half * 32 + g) * SY_STR + t;
             const double* AJ = (I == J ? cur : cur + 64 * SY_STR) + g * SY_STR + t;
@@ -113,7 +120,6 @@ __global__ void __launch_bounds__(SY_THREADS, 1) syrk_kernel(const double* A, co
 #pragma unroll
             for (int ks = 0; ks < SY_KC / 4; ++ks) dmma(am, AIw[ks * 4], mb[ks * 4 * SY_MUB]);
         }
-        __syncthreads();
     }
     if (do_mraw) {
         const int row = I * 64 + warp * 8 + g;
@@ -152,7 +158,7 @@ void syrk_accumulate(const LayerDev& ly, const ChunkBuffers& cb, double* part, d
     int ns = nsplit;
     if (ns > nchunks) ns = (int)nchunks;
     const int64_t per_split = (nchunks + ns - 1) / ns * SY_KC;
-    const size_t smem = 2 * SY_STAGE * sizeof(double);
+    const size_t smem = (size_t)SY_NSTAGE * SY_STAGE * sizeof(double);
     cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid(npairs, ns, kgroups);
     syrk_kernel<<<grid, SY_THREADS, smem, ln.stream>>>(cb.A, cb.vbar, cb.mubar, part, mraw_part, ly.Mp, ly.K, cb.ldn, cb.n,

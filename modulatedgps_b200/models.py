@@ -28,7 +28,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, parallel
 from .broadcasting_lik import BroadcastingLikelihood
 from .likelihoods import GaussianModified
 from .parameter import F64, FillTriangular, Module, Parameter, to_device_f64
@@ -331,13 +331,8 @@ class SMGP(SGP):
         alik_var = self._assign_lik_variances(K)
         # global batch size / Philox offset of this shard
         if self._dp:
-            import torch.distributed as dist
             if n_global is None or point_offset is None:
-                counts = torch.zeros(dist.get_world_size(self.process_group), dtype=torch.int64, device=dev)
-                counts[dist.get_rank(self.process_group)] = N
-                dist.all_reduce(counts, group=self.process_group)
-                n_global = int(counts.sum())
-                point_offset = int(counts[:dist.get_rank(self.process_group)].sum())
+                n_global, point_offset = parallel.global_count_and_offset(N, self.process_group, dev)
         else:
             n_global = N if n_global is None else int(n_global)
             point_offset = 0 if point_offset is None else int(point_offset)
@@ -361,11 +356,10 @@ class SMGP(SGP):
         galik = torch.zeros(K, dtype=F64, device=dev)
         lib, h = ctx.lib, ctx.handle
         if self._dp:
-            import torch.distributed as dist
             rb = torch.empty(int(lib.mgp_reduce_buffer_len(C.byref(pv.struct), C.byref(av.struct))), dtype=F64, device=dev)
             ctx.check(lib.mgp_elbo_local(h, C.byref(cfg), C.byref(pv.struct), C.byref(av.struct), _lib.ptr(lik_var),
                                          _lib.ptr(alik_var), _lib.ptr(Xd), _lib.ptr(Yd), N, C.byref(nz), _lib.ptr(rb)))
-            dist.all_reduce(rb, group=self.process_group)          # the single fused collective of the step
+            parallel.all_reduce_sum_(rb, self.process_group)        # the single fused collective of the step
             ctx.check(lib.mgp_elbo_finish(h, C.byref(cfg), C.byref(pv.struct), C.byref(av.struct), _lib.ptr(lik_var),
                                           _lib.ptr(alik_var), _lib.ptr(rb), _lib.ptr(elbo), C.byref(pgs), C.byref(ags),
                                           _lib.ptr(glik), _lib.ptr(galik)))

@@ -25,8 +25,11 @@ struct Buf {
 struct LayerSlot {
     LayerDev dev{};
     Buf inv_ls, Zs_rm, Zs_fm, zs2, Kuu, L, Linv, W_Linv, W_LinvT, Lq_rm, W_LqT, Q_rm, W_Lq, W_m, W_mT, T1, T2, T3, Sfull, rowout;
-    Buf A, Bk, asq, fmean, fvar, mubar, vbar;   // chunk buffers
+    Buf A, Bk, fmean, fvar, mubar, vbar;   // chunk buffers
     Buf syrk_part, mraw_part, esum_part;    // per-CTA partial sums
+    Buf syrk_plan;                          // SyrkWork[] of the current (Mp, K, chunk length)
+    int64_t plan_key[3] = {-1, -1, -1};
+    int plan_len = 0;
     int nsplit = 0, esum_nparts = 0;
 };
 
@@ -192,22 +195,39 @@ int setup_layer(mgp_ctx* c, LayerSlot& s, const mgp_layer* l, bool need_bwd) {
 
 int ensure_chunk(mgp_ctx* c, LayerSlot& s, int64_t ldn, bool need_bwd) {
     const size_t Mp = s.dev.Mp, K = s.dev.K;
-    TRY(ensure(c, s.A, Mp * (size_t)ldn * 8, true));
-    TRY(ensure(c, s.asq, (size_t)ldn * 8, true));
+    const size_t tw = layer_tile_width(s.dev.Mp, s.dev.Dp, s.dev.K);
+    const size_t tiled = ((size_t)ldn / tw) * Mp * (tw + 4) * 8;   // tile-major [ldn/tw][Mp][tw+4]
+    TRY(ensure(c, s.A, tiled, true));
     TRY(ensure(c, s.fmean, (size_t)ldn * K * 8, true));
     TRY(ensure(c, s.fvar, (size_t)ldn * K * 8, true));
     if (need_bwd) {
-        TRY(ensure(c, s.Bk, K * Mp * (size_t)ldn * 8, true));
+        TRY(ensure(c, s.Bk, K * tiled, true));
         TRY(ensure(c, s.mubar, (size_t)ldn * K * 8, true));
         TRY(ensure(c, s.vbar, (size_t)ldn * K * 8, true));
     }
     return MGP_OK;
 }
 
+// (re)build the SYRK work plan of this layer for chunks of n points; uploaded only when (Mp, K, n) change
+int ensure_syrk_plan(mgp_ctx* c, LayerSlot& s, int64_t n) {
+    const int kc = layer_tile_width(s.dev.Mp, s.dev.Dp, s.dev.K);
+    const int64_t key[3] = {s.dev.Mp, (int64_t)s.dev.K * 64 + kc, n};
+    if (s.syrk_plan.p && key[0] == s.plan_key[0] && key[1] == s.plan_key[1] && key[2] == s.plan_key[2]) return MGP_OK;
+    std::vector<SyrkWork> plan;
+    s.plan_len = syrk_make_plan(s.dev.Mp, s.dev.K, n, kc, c->num_sms, plan);
+    TRY(ensure(c, s.syrk_plan, plan.size() * sizeof(SyrkWork)));
+    // pageable source: the copy is staged before the call returns, so `plan` may go out of scope
+    CUDA_TRY(c, cudaMemcpyAsync(s.syrk_plan.p, plan.data(), plan.size() * sizeof(SyrkWork), cudaMemcpyHostToDevice, c->stream));
+    for (int i = 0; i < 3; ++i) s.plan_key[i] = key[i];
+    return MGP_OK;
+}
+
 ChunkBuffers chunk_of(const LayerSlot& s, const double* X, int64_t n, int64_t ldn) {
     ChunkBuffers cb;
     cb.n = n; cb.ldn = ldn; cb.X = X;
-    cb.A = (double*)s.A.p; cb.Bk = nullptr; cb.asq = (double*)s.asq.p; cb.fmean = (double*)s.fmean.p; cb.fvar = (double*)s.fvar.p;
+    cb.tw = layer_tile_width(s.dev.Mp, s.dev.Dp, s.dev.K);
+    cb.tiles_cap = ldn / cb.tw;
+    cb.A = (double*)s.A.p; cb.Bk = nullptr; cb.fmean = (double*)s.fmean.p; cb.fvar = (double*)s.fvar.p;
     cb.mubar = (double*)s.mubar.p; cb.vbar = (double*)s.vbar.p;
     return cb;
 }
@@ -333,8 +353,9 @@ void mgp_ctx_destroy(mgp_ctx* c) {
     auto rel = [](Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; };
     for (auto& s : c->slot) {
         Buf* all[] = {&s.inv_ls, &s.Zs_rm, &s.Zs_fm, &s.zs2, &s.Kuu, &s.L, &s.Linv, &s.W_Linv, &s.W_LinvT, &s.Lq_rm,
-                      &s.W_LqT, &s.Q_rm, &s.W_Lq, &s.W_m, &s.W_mT, &s.T1, &s.T2, &s.T3, &s.Sfull, &s.rowout, &s.A, &s.Bk, &s.asq,
-                      &s.fmean, &s.fvar, &s.mubar, &s.vbar, &s.syrk_part, &s.mraw_part, &s.esum_part};
+                      &s.W_LqT, &s.Q_rm, &s.W_Lq, &s.W_m, &s.W_mT, &s.T1, &s.T2, &s.T3, &s.Sfull, &s.rowout, &s.A, &s.Bk,
+                      &s.fmean, &s.fvar, &s.mubar, &s.vbar, &s.syrk_part, &s.mraw_part, &s.esum_part,
+                      &s.syrk_plan};
         for (Buf* b : all) rel(*b);
     }
     rel(c->mc_part); rel(c->scratch_rb); rel(c->kl); rel(c->status);
@@ -550,8 +571,10 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
             mc_pass(m, (double*)c->mc_part.p, ln);
             mc_fold((double*)c->mc_part.p, mc_num_blocks(ldc), reduce_buf, ln);
         }
-        { Timed t(c, ST_SYRK); syrk_accumulate(sp.dev, cp, (double*)sp.syrk_part.p, (double*)sp.mraw_part.p, sp.nsplit, ln); }
-        { Timed t(c, ST_SYRK); syrk_accumulate(sa.dev, ca, (double*)sa.syrk_part.p, (double*)sa.mraw_part.p, sa.nsplit, ln); }
+        TRY(ensure_syrk_plan(c, sp, n));
+        TRY(ensure_syrk_plan(c, sa, n));
+        { Timed t(c, ST_SYRK); syrk_accumulate(sp.dev, cp, (const SyrkWork*)sp.syrk_plan.p, sp.plan_len, (double*)sp.syrk_part.p, (double*)sp.mraw_part.p, ln); }
+        { Timed t(c, ST_SYRK); syrk_accumulate(sa.dev, ca, (const SyrkWork*)sa.syrk_plan.p, sa.plan_len, (double*)sa.syrk_part.p, (double*)sa.mraw_part.p, ln); }
         { Timed t(c, ST_COND_BWD_A); cond_bwd_a(sp.dev, cp, ln); }
         { Timed t(c, ST_COND_BWD_B); cond_bwd_b(sp.dev, cp, (double*)sp.esum_part.p, maxparts, &sp.esum_nparts, ln); }
         { Timed t(c, ST_COND_BWD_A); cond_bwd_a(sa.dev, ca, ln); }

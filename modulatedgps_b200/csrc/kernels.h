@@ -36,11 +36,12 @@ void gemm_small(int m, int n, int k, double alpha, const double* A, int lda, int
 // ---- stream_kernels.cu : the N-streaming DMMA kernels ------------------------------------------------
 struct ChunkBuffers {
     int64_t n;        // valid points in this chunk
-    int64_t ldn;      // padded length (multiple of 64): leading dimension of the [Mp, ldn] arrays
+    int64_t ldn;      // padded length (multiple of 64) of the per-point arrays
+    int tw;           // tile width of the tile-major workspace (layer_tile_width): 32 or 16 points
+    int64_t tiles_cap;  // ldn / tw: tiles per component in Bk
     const double* X;  // [n, D] this chunk's rows
-    double* A;        // [Mp, ldn]  A = L^-1 Kuf  (overwritten by Abar in the backward)
-    double* Bk;       // [K, Mp, ldn] B_k = Lq_k^T A, kept for the backward (null on forward-only paths)
-    double* asq;      // [ldn]      |a_n|^2
+    double* A;        // tile-major [ldn/tw][Mp][tw+4]  A = L^-1 Kuf  (overwritten by Abar in the backward)
+    double* Bk;       // [K] x tile-major: B_k = Lq_k^T A, kept for the backward (null on forward-only paths)
     double* fmean;    // [ldn, K]
     double* fvar;     // [ldn, K]
     double* mubar;    // [ldn, K]   d/d fmean
@@ -56,13 +57,26 @@ void cond_bwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln);
 void cond_bwd_b(const LayerDev& ly, const ChunkBuffers& cb, double* esum_part, int nparts_cap, int* nparts,
                 const Launch& ln);
 int stream_max_parts(const Launch& ln);
+// tile width (points) of a layer's tile-major workspace: 32 while two [Mp x 36] tiles fit in shared memory, else 16
+int layer_tile_width(int Mp, int Dp, int K);
 
 // ---- syrk.cu : S_k += A diag(vbar_k) A^T ----------------------------------------------------------------
-// part: [nsplit, K, Mp, Mp]; each CTA accumulates into its own slot (deterministic); lower 64x64 tiles only.
-// mraw_part: [nsplit, Mp, KP] += A mubar (computed by the J == 0 tile column, which sees every row of A).
-void syrk_accumulate(const LayerDev& ly, const ChunkBuffers& cb, double* part, double* mraw_part, int nsplit,
-                     const Launch& ln);
-int syrk_num_splits(int Mp, int K, const Launch& ln);
+// One CTA per work item: 64x64 tile pair (I >= J) of S, component group kbase..kbase+3, points [pbeg, pend), and the
+// slot of `part` it accumulates into.  The plan is built on the host (syrk_make_plan) whenever (Mp, K, n) change.
+struct SyrkWork {
+    int I, J, kbase, slot;
+    int64_t pbeg, pend;
+};
+// part: [nslots, K, Mp, Mp]; each CTA accumulates into its own slot (deterministic); fragments with col <= row of the
+// lower 64x64 tiles only.  mraw_part: [nslots, Mp, KP] += A mubar (computed by the J == 0 tile column, which sees
+// every row of A).
+void syrk_accumulate(const LayerDev& ly, const ChunkBuffers& cb, const SyrkWork* d_plan, int nwork, double* part,
+                     double* mraw_part, const Launch& ln);
+int syrk_num_splits(int Mp, int K, const Launch& ln);   // number of slots
+}  // namespace mgp
+#include <vector>
+namespace mgp {
+int syrk_make_plan(int Mp, int K, int64_t n, int kc, int num_sms, std::vector<SyrkWork>& plan);
 
 // ---- mc_pass.cu : fused Monte-Carlo likelihood pass, forward + adjoints ------------------------------
 struct McArgs {

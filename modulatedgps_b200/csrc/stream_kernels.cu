@@ -1,16 +1,22 @@
 // The N-streaming FP64 tensor-core kernels of the SVGP conditional, forward and backward.
 //
-// Every kernel has the same shape: a persistent CTA walks over tiles of NT points; per tile it stages one
-// [Mp x NT] right operand T in shared memory (generated RBF cross-covariances, or a slab of a materialised
-// [Mp, N] array), and each warp computes 16-row blocks  C = W[rows, k-range] * T  on DMMA.8x8x4 with the
-// left operand W streamed from L2 in fragment-major order (one coalesced 256-byte load per fragment).
-// Triangular left operands only visit their non-zero k-range; 16-row blocks are dealt to the 8 warps in
-// snake order so that the triangular work is balanced.
+// Layout.  The [Mp x N] workspace arrays A = L^-1 Kuf and B_k = Lq_k^T A are stored TILE-MAJOR: tile ti (NT points)
+// is one contiguous [Mp][NT + 4] block — exactly the shared-memory image the kernels multiply from (row stride
+// NT + 4 == 4 mod 16 doubles => conflict-free B-fragment LDS.64).  A whole right operand is therefore fetched by ONE
+// cp.async.bulk (TMA, UBLKCP) completing on an mbarrier.
 //
-//   cond_fwd_a : T = Kuf tile (r^2 contraction on DMMA + exp)   A = L^-1 T            -> A, |a_n|^2
-//   cond_fwd_b : T = A tile        B_k = Lq_k^T T (norms only), mean = q_mu^T T       -> fmean, fvar
-//   cond_bwd_a : T = B_k tiles     Abar = sum_k Lq_k T_k diag(2 vbar_k) + q_mu mubar^T - 2 A diag(sum vbar)  -> Abar (over A)
-//   cond_bwd_b : T = Abar tile     Kuf_bar = L^-T T ; E = Kuf_bar .* Kuf              -> sums E [1, xs, xs^2]
+// Structure.  One persistent CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Right operands move
+// through a ring of NBUF shared-memory buffers guarded by full[] / done[] mbarriers; there is no CTA-wide barrier in
+// the steady state.  Warps 0-7 are DMMA consumers: each computes 16-row blocks  C = W[rows, k-range] * T  on
+// DMMA.8x8x4 with the left operand W streamed from L2 in fragment-major order (one coalesced 256-byte load per
+// fragment, software-pipelined across block / component / tile boundaries).  Triangular left operands only visit
+// their non-zero k-range; 16-row blocks are dealt to the 8 warps in snake order so the triangular work balances.
+// Extra warps feed the ring and take the per-tile epilogues off the consumers:
+//
+//   cond_fwd_a : warps 8-11 generate the Kuf tile (r^2 contraction on DMMA + exp)   A = L^-1 Kuf        -> A
+//   cond_fwd_b : warp 8 loads the A tile, reduces the per-warp partial norms         B_k = Lq_k^T A      -> B_k, fmean, fvar
+//   cond_bwd_a : warp 8 loads B_0..B_{K-1}, A and the adjoint slabs of the tile       Abar (see below)    -> Abar (over A)
+//   cond_bwd_b : warp 8 loads the Abar tile and stages X                              E = (L^-T Abar) .* Kuf -> sums E [1, xs, xs^2]
 //
 // Reference arithmetic replaced: gpflow SquaredExponential.K + base_conditional as called from
 // IndependentPosteriorSingleOutputModified._conditional_fused (MixtureGPs/models.py:129-144), evaluated once
@@ -23,8 +29,8 @@
 
 namespace mgp {
 
-constexpr int SK_WARPS = 8;
-constexpr int SK_THREADS = SK_WARPS * 32;
+constexpr int SK_WARPS = 8;                    // DMMA consumer warps
+constexpr int SK_CTHREADS = SK_WARPS * 32;
 
 __host__ __device__ inline int xs_stride(int Dp) { return ((Dp - 4 + 15) / 16) * 16 + 4; }
 
@@ -33,69 +39,10 @@ __device__ __forceinline__ int snake_block(int round, int warp, int nb16) {
     const int b = round * SK_WARPS + ((round & 1) ? (SK_WARPS - 1 - warp) : warp);
     return b < nb16 ? b : -1;
 }
-
-// acc[2][NF][2] += W[rows 8*rb8 .. +16, k4-blocks kb0..kb1) * T[(kb*4 ..), :]
-// Wf points at k4-block 0 of this segment for row-block 0; C4 = total k4-blocks per row-block of W.
-// SCALED: right-operand column (nf*8+g) is multiplied by sc[nf] (diag(vbar_k) folded into the B fragment).
-template <int NT, bool SCALED>
-__device__ __forceinline__ void wgemm_block(const double* __restrict__ Wf, int C4, int rb8, int kb0, int kb1,
-                                            const double* Tsm, double (&acc)[2][NT / 8][2],
-                                            const double (&sc)[NT / 8], int lane) {
-    constexpr int NF = NT / 8, STR = NT + 4;
-    const int g = lane >> 2, t = lane & 3;
-    const double* w0 = Wf + ((size_t)rb8 * C4) * 32 + lane;
-    const double* w1 = w0 + (size_t)C4 * 32;
-    const double* tb = Tsm + t * STR + g;
-    int kb = kb0;
-    const int ngroups = (kb1 - kb0) >> 2;
-    double a0[4], a1[4];
-    if (ngroups > 0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            a0[j] = __ldg(w0 + (size_t)(kb + j) * 32);
-            a1[j] = __ldg(w1 + (size_t)(kb + j) * 32);
-        }
-    }
-    for (int it = 0; it < ngroups; ++it) {
-        double n0[4], n1[4];
-        if (it + 1 < ngroups) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                n0[j] = __ldg(w0 + (size_t)(kb + 4 + j) * 32);
-                n1[j] = __ldg(w1 + (size_t)(kb + 4 + j) * 32);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double* tr = tb + (size_t)(kb + j) * 4 * STR;
-#pragma unroll
-            for (int nf = 0; nf < NF; ++nf) {
-                double b = tr[nf * 8];
-                if (SCALED) b *= sc[nf];
-                dmma(acc[0][nf], a0[j], b);
-                dmma(acc[1][nf], a1[j], b);
-            }
-        }
-        if (it + 1 < ngroups) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                a0[j] = n0[j];
-                a1[j] = n1[j];
-            }
-        }
-        kb += 4;
-    }
-    for (; kb < kb1; ++kb) {
-        const double x0 = __ldg(w0 + (size_t)kb * 32), x1 = __ldg(w1 + (size_t)kb * 32);
-        const double* tr = tb + (size_t)kb * 4 * STR;
-#pragma unroll
-        for (int nf = 0; nf < NF; ++nf) {
-            double b = tr[nf * 8];
-            if (SCALED) b *= sc[nf];
-            dmma(acc[0][nf], x0, b);
-            dmma(acc[1][nf], x1, b);
-        }
-    }
+// number of 16-row blocks dealt to this warp (only the last snake round can be short)
+__device__ __forceinline__ int my_block_count(int warp, int nb16) {
+    const int R = (nb16 + SK_WARPS - 1) / SK_WARPS;
+    return R == 0 ? 0 : (snake_block(R - 1, warp, nb16) >= 0 ? R : R - 1);
 }
 
 template <int NF>
@@ -104,12 +51,6 @@ __device__ __forceinline__ void zero_acc(double (&acc)[2][NF][2]) {
     for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
         for (int nf = 0; nf < NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
-}
-
-// number of 16-row blocks dealt to this warp (only the last snake round can be short)
-__device__ __forceinline__ int my_block_count(int warp, int nb16) {
-    const int R = (nb16 + SK_WARPS - 1) / SK_WARPS;
-    return R == 0 ? 0 : (snake_block(R - 1, warp, nb16) >= 0 ? R : R - 1);
 }
 
 // ---- cross-segment software pipelining of the left-operand fragments ------------------------------------------
@@ -159,24 +100,24 @@ __device__ __forceinline__ void wgemm_seg(const Seg& cur, int kb1, int C4, const
     }
 }
 
-// Xs[n][d] = X[n0+n][d] / lengthscale_d (0 outside the chunk / padding); xs2[n] = |Xs_n|^2
+// Xs[n][d] = X[n0+n][d] / lengthscale_d (0 outside the chunk / padding); xs2[n] = |Xs_n|^2.  One warp.
 template <int NT>
-__device__ __forceinline__ void stage_x(const LayerDev& ly, const ChunkBuffers& cb, int64_t n0, double* Xs,
-                                        double* xs2) {
+__device__ __forceinline__ void stage_x_warp(const LayerDev& ly, const ChunkBuffers& cb, int64_t n0, double* Xs,
+                                             double* xs2, int lane) {
     const int Dp = ly.Dp, D = ly.D, XSTR = xs_stride(Dp);
-    for (int idx = threadIdx.x; idx < NT * Dp; idx += SK_THREADS) {
+    for (int idx = lane; idx < NT * Dp; idx += 32) {
         const int n = idx / Dp, d = idx % Dp;
         double v = 0.0;
         if (n0 + n < cb.n && d < D) v = cb.X[(size_t)(n0 + n) * D + d] / ly.lengthscales[ly.n_ls == 1 ? 0 : d];
         Xs[n * XSTR + d] = v;
     }
-    __syncthreads();
-    for (int n = threadIdx.x; n < NT; n += SK_THREADS) {
+    __syncwarp();
+    for (int n = lane; n < NT; n += 32) {
         double s = 0.0;
         for (int d = 0; d < Dp; ++d) s += Xs[n * XSTR + d] * Xs[n * XSTR + d];
         xs2[n] = s;
     }
-    __syncthreads();
+    __syncwarp();
 }
 
 // Kuf values of the 8-row block rb8 in C-fragment layout: kv[nf][e] = k(z_{8 rb8+g}, x_{nf*8+2t+e}).
@@ -206,31 +147,31 @@ __device__ __forceinline__ void gen_kuf_block(const LayerDev& ly, int rb8, const
         }
 }
 
-// T[:, 0..NT) <- G[:, n0 .. n0+NT)  for a row-major [Mp, ldn] array (16-byte cp.async)
-template <int NT>
-__device__ __forceinline__ void load_tile_async(double* T, const double* G, int Mp, int64_t ldn, int64_t n0) {
-    constexpr int STR = NT + 4, C2 = NT / 2;
-    for (int idx = threadIdx.x; idx < Mp * C2; idx += SK_THREADS) {
-        const int row = idx / C2, c2 = idx % C2;
-        cp_async16(T + (size_t)row * STR + 2 * c2, G + (size_t)row * ldn + n0 + 2 * c2);
-    }
-    cp_async_commit();
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// shared-memory carve-up helper: mbarriers live at the front of dynamic smem (16-byte aligned region)
+constexpr int SK_BAR_DOUBLES = 8;   // room for 2 x NBUF mbarriers (NBUF <= 2) + padding
+
 // ==================================================================================================
-// cond_fwd_a
+// cond_fwd_a :  A tile = L^-1 * Kuf tile
+// Two CTAs per SM (16 warps): every warp first generates rows of the Kuf tile (exp on the FP64 pipe), then
+// multiplies.  The generation phase is scalar FP64 work that shares the pipe with DMMA, so it wants MANY warps to
+// overlap with the other CTA's DMMA phase — a dedicated generator-warp ring starves behind the consumers' DMMAs
+// (measured: 9.1 ms vs 6.2 ms for this form at config #4).
 // ==================================================================================================
 template <int NT>
-__global__ void __launch_bounds__(SK_THREADS) cond_fwd_a_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
+__global__ void __launch_bounds__(SK_CTHREADS) cond_fwd_a_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
     constexpr int NF = NT / 8, STR = NT + 4;
     extern __shared__ __align__(16) double smem[];
     const int Mp = ly.Mp, XSTR = xs_stride(ly.Dp);
     double* T = smem;
     double* Xs = T + (size_t)Mp * STR;
     double* xs2 = Xs + NT * XSTR;
-    double* colpart = xs2 + NT;  // [SK_WARPS][NT]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nb16 = Mp / 16, nb8 = Mp / 8, C4 = Mp / 4;
+    const size_t tile_elems = (size_t)Mp * STR;
     const double variance = ly.variance[0];
     const int nmy = my_block_count(warp, nb16);
     auto seg_of = [&](int i) { const int b = snake_block(i, warp, nb16); return Seg{ly.W_Linv, 2 * b, 0}; };
@@ -239,7 +180,9 @@ __global__ void __launch_bounds__(SK_THREADS) cond_fwd_a_kernel(LayerDev ly, Chu
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t n0 = (int64_t)tile * NT;
-        stage_x<NT>(ly, cb, n0, Xs, xs2);
+        double* Aout = cb.A + (size_t)tile * tile_elems;
+        if (warp == 0) stage_x_warp<NT>(ly, cb, n0, Xs, xs2, lane);
+        __syncthreads();
         for (int rb = warp; rb < nb8; rb += SK_WARPS) {
             double kv[NF][2];
             gen_kuf_block<NT>(ly, rb, Xs, xs2, variance, kv, lane);
@@ -248,9 +191,6 @@ __global__ void __launch_bounds__(SK_THREADS) cond_fwd_a_kernel(LayerDev ly, Chu
                 *reinterpret_cast<double2*>(T + (size_t)(rb * 8 + g) * STR + nf * 8 + 2 * t) = make_double2(kv[nf][0], kv[nf][1]);
         }
         __syncthreads();
-        double colsq[NF][2];
-#pragma unroll
-        for (int nf = 0; nf < NF; ++nf) colsq[nf][0] = colsq[nf][1] = 0.0;
         for (int i = 0; i < nmy; ++i) {
             const int b = snake_block(i, warp, nb16);
             double acc[2][NF][2];
@@ -259,81 +199,126 @@ __global__ void __launch_bounds__(SK_THREADS) cond_fwd_a_kernel(LayerDev ly, Chu
 #pragma unroll
             for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
-                for (int nf = 0; nf < NF; ++nf) {
-                    const size_t row = (size_t)(b * 16 + mf * 8 + g);
-                    *reinterpret_cast<double2*>(cb.A + row * cb.ldn + n0 + nf * 8 + 2 * t) =
+                for (int nf = 0; nf < NF; ++nf)
+                    *reinterpret_cast<double2*>(Aout + (size_t)(b * 16 + mf * 8 + g) * STR + nf * 8 + 2 * t) =
                         make_double2(acc[mf][nf][0], acc[mf][nf][1]);
-                    colsq[nf][0] += acc[mf][nf][0] * acc[mf][nf][0];
-                    colsq[nf][1] += acc[mf][nf][1] * acc[mf][nf][1];
-                }
-        }
-#pragma unroll
-        for (int nf = 0; nf < NF; ++nf)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const double s = sum_over_g(colsq[nf][e]);
-                if (g == 0) colpart[warp * NT + nf * 8 + 2 * t + e] = s;
-            }
-        __syncthreads();
-        for (int n = threadIdx.x; n < NT; n += SK_THREADS) {
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < SK_WARPS; ++w) s += colpart[w * NT + n];
-            cb.asq[n0 + n] = s;
         }
         __syncthreads();
     }
 }
 
 // ==================================================================================================
-// cond_fwd_b
+// cond_fwd_b :  B_k = Lq_k^T A (kept for the backward), fvar = variance - |a|^2 + sum_m B_k^2, fmean = q_mu^T A
+// warps 0-7 multiply and leave per-warp partial column sums; warp 8 loads tiles and finishes the sums
 // ==================================================================================================
-template <int NT>
-__global__ void __launch_bounds__(SK_THREADS) cond_fwd_b_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
+template <int NT, int NBUF>
+__global__ void __launch_bounds__(SK_CTHREADS + 32, 1) cond_fwd_b_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
     constexpr int NF = NT / 8, STR = NT + 4;
     extern __shared__ __align__(16) double smem[];
     const int Mp = ly.Mp, K = ly.K;
-    double* T = smem;
-    double* colpart = T + (size_t)Mp * STR;  // [SK_WARPS][KP][NT]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* done = full + NBUF;
+    double* Tb = smem + SK_BAR_DOUBLES;                          // [NBUF][Mp][STR]
+    double* sqpart = Tb + (size_t)NBUF * Mp * STR;               // [NBUF][SK_WARPS][K][NT]  partial sum_m B_k^2
+    double* mnpart = sqpart + (size_t)NBUF * SK_WARPS * K * NT;  // [NBUF][SK_WARPS][K][NT]  partial q_mu^T A
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nb16 = Mp / 16, C4 = Mp / 4;
-    const double variance = ly.variance[0];
+    const size_t tile_elems = (size_t)Mp * STR;
+    const unsigned tile_bytes = (unsigned)(tile_elems * sizeof(double));
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], SK_WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto tile_of = [&](int i) { return (int64_t)blockIdx.x + (int64_t)i * gridDim.x; };
+
+    if (warp == SK_WARPS) {   // ---- loader + finisher ----
+        auto issue = [&](int i) {
+            if (lane == 0) {
+                const int buf = i % NBUF;
+                mbar_arrive_expect_tx(&full[buf], tile_bytes);
+                bulk_g2s(Tb + (size_t)buf * tile_elems, cb.A + (size_t)tile_of(i) * tile_elems, tile_bytes, &full[buf]);
+            }
+        };
+        for (int i = 0; i < NBUF && i < my_tiles; ++i) issue(i);
+        const double variance = ly.variance[0];
+        for (int i = 0; i < my_tiles; ++i) {
+            const int buf = i % NBUF;
+            const int64_t n0 = tile_of(i) * NT;
+            const double* T = Tb + (size_t)buf * tile_elems;
+            // |a_n|^2 of this lane's column(s) while the consumers are still multiplying (the tile has landed once
+            // full[buf] completes; waiting on it here is harmless)
+            mbar_wait(&full[buf], (unsigned)((i / NBUF) & 1));
+            double asq[(NT + 31) / 32];
+#pragma unroll
+            for (int c = 0; c < (NT + 31) / 32; ++c) asq[c] = 0.0;
+            if (lane < NT) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                for (int m = 0; m < Mp; m += 4) {
+                    const double v0 = T[(size_t)m * STR + lane], v1 = T[(size_t)(m + 1) * STR + lane];
+                    const double v2 = T[(size_t)(m + 2) * STR + lane], v3 = T[(size_t)(m + 3) * STR + lane];
+                    s0 = fma(v0, v0, s0); s1 = fma(v1, v1, s1); s2 = fma(v2, v2, s2); s3 = fma(v3, v3, s3);
+                }
+                asq[0] = (s0 + s1) + (s2 + s3);
+            }
+            mbar_wait(&done[buf], (unsigned)((i / NBUF) & 1));   // every consumer has left its partials and the tile
+            const double* sq = sqpart + (size_t)buf * SK_WARPS * K * NT;
+            const double* mn = mnpart + (size_t)buf * SK_WARPS * K * NT;
+            if (lane < NT) {
+                for (int k = 0; k < K; ++k) {
+                    double s = 0.0, m = 0.0;
+#pragma unroll
+                    for (int w = 0; w < SK_WARPS; ++w) {
+                        s += sq[((size_t)w * K + k) * NT + lane];
+                        m += mn[((size_t)w * K + k) * NT + lane];
+                    }
+                    cb.fvar[(size_t)(n0 + lane) * K + k] = (variance - asq[0]) + s;   // Knn - sum A^2 + sum LTA^2
+                    cb.fmean[(size_t)(n0 + lane) * K + k] = m;
+                }
+            }
+            __syncwarp();
+            if (i + NBUF < my_tiles) issue(i + NBUF);
+        }
+        return;
+    }
+    // ---- consumers ----
     const int nmy = my_block_count(warp, nb16);
-    const bool does_mean = (warp == SK_WARPS - 1);
-    const Seg mean_seg{ly.W_mT, 0, 0};
-    auto seg_of = [&](int k, int i) {
-        const int b = snake_block(i, warp, nb16);
+    // the fmean contraction is split over the warps by k-range: warp w takes k4-blocks [w C4/8, (w+1) C4/8)
+    const int mkb0 = warp * (C4 / SK_WARPS), mkb1 = mkb0 + C4 / SK_WARPS;   // C4 = Mp/4 is a multiple of 8
+    auto seg_of = [&](int k, int r) {
+        const int b = snake_block(r, warp, nb16);
         return Seg{ly.W_LqT + (size_t)k * Mp * Mp, 2 * b, 4 * b};
     };
-    auto first_seg = [&]() { return nmy > 0 ? seg_of(0, 0) : mean_seg; };
     WFrag wf;
-    if (nmy > 0 || does_mean) { const Seg s0 = first_seg(); wfrag_load(wf, s0, C4, s0.kb0, lane); }
-
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t n0 = (int64_t)tile * NT;
-        load_tile_async<NT>(T, cb.A, Mp, cb.ldn, n0);
-        cp_async_wait<0>();
-        __syncthreads();
+    if (nmy > 0) { const Seg s0 = seg_of(0, 0); wfrag_load(wf, s0, C4, s0.kb0, lane); }
+    for (int i = 0; i < my_tiles; ++i) {
+        const int buf = i % NBUF;
+        const int64_t tile = tile_of(i);
+        const double* T = Tb + (size_t)buf * tile_elems;
+        double* sq = sqpart + ((size_t)buf * SK_WARPS + warp) * K * NT;
+        double* mn = mnpart + ((size_t)buf * SK_WARPS + warp) * K * NT;
+        mbar_wait(&full[buf], (unsigned)((i / NBUF) & 1));
         for (int k = 0; k < K; ++k) {
             double colsq[NF][2];
 #pragma unroll
             for (int nf = 0; nf < NF; ++nf) colsq[nf][0] = colsq[nf][1] = 0.0;
-            for (int i = 0; i < nmy; ++i) {
-                const int b = snake_block(i, warp, nb16);
+            double* Bk = cb.Bk ? cb.Bk + ((size_t)k * cb.tiles_cap + tile) * tile_elems : nullptr;
+            for (int r = 0; r < nmy; ++r) {
+                const int b = snake_block(r, warp, nb16);
                 double acc[2][NF][2];
                 zero_acc<NF>(acc);
-                const Seg nxt = (i + 1 < nmy) ? seg_of(k, i + 1) : (k + 1 < K ? seg_of(k + 1, 0) : (does_mean ? mean_seg : seg_of(0, 0)));
-                wgemm_seg<NT>(seg_of(k, i), C4, C4, T, acc, lane, wf, nxt);   // upper triangular
-                double* Bk = cb.Bk ? cb.Bk + (size_t)k * Mp * cb.ldn : nullptr;
+                const Seg nxt = (r + 1 < nmy) ? seg_of(k, r + 1) : seg_of(k + 1 < K ? k + 1 : 0, 0);
+                wgemm_seg<NT>(seg_of(k, r), C4, C4, T, acc, lane, wf, nxt);   // upper triangular
 #pragma unroll
                 for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
                     for (int nf = 0; nf < NF; ++nf) {
                         if (Bk)   // kept for the backward: Abar needs Lq_k (2 B_k diag(vbar_k))
-                            *reinterpret_cast<double2*>(Bk + (size_t)(b * 16 + mf * 8 + g) * cb.ldn + n0 + nf * 8 + 2 * t) =
+                            *reinterpret_cast<double2*>(Bk + (size_t)(b * 16 + mf * 8 + g) * STR + nf * 8 + 2 * t) =
                                 make_double2(acc[mf][nf][0], acc[mf][nf][1]);
-                        colsq[nf][0] += acc[mf][nf][0] * acc[mf][nf][0];
-                        colsq[nf][1] += acc[mf][nf][1] * acc[mf][nf][1];
+                        colsq[nf][0] = fma(acc[mf][nf][0], acc[mf][nf][0], colsq[nf][0]);
+                        colsq[nf][1] = fma(acc[mf][nf][1], acc[mf][nf][1], colsq[nf][1]);
                     }
             }
 #pragma unroll
@@ -341,175 +326,219 @@ __global__ void __launch_bounds__(SK_THREADS) cond_fwd_b_kernel(LayerDev ly, Chu
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const double s = sum_over_g(colsq[nf][e]);
-                    if (g == 0) colpart[((size_t)warp * KP + k) * NT + nf * 8 + 2 * t + e] = s;
+                    if (g == 0) sq[(size_t)k * NT + nf * 8 + 2 * t + e] = s;
                 }
         }
-        if (does_mean) {  // fmean^T [K x NT] = q_mu^T [K x Mp] * A tile
-            double acc[2][NF][2];
-            zero_acc<NF>(acc);
-            wgemm_seg<NT>(mean_seg, C4, C4, T, acc, lane, wf, first_seg());
+        {   // this warp's slice of fmean^T [K x NT] = q_mu^T [K x Mp] * A tile   (rows >= K of W_mT are zero)
+            double acc[NF][2];
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf) acc[nf][0] = acc[nf][1] = 0.0;
+            const double* wm = ly.W_mT + (size_t)mkb0 * 32 + lane;
+            const double* tb = T + t * STR + g;
+            for (int kb = mkb0; kb < mkb1; ++kb) {
+                const double a = __ldg(wm + (size_t)(kb - mkb0) * 32);
+                const double* tr = tb + (size_t)kb * 4 * STR;
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) dmma(acc[nf], a, tr[nf * 8]);
+            }
             if (g < K) {
 #pragma unroll
                 for (int nf = 0; nf < NF; ++nf)
-#pragma unroll
-                    for (int e = 0; e < 2; ++e)
-                        cb.fmean[(size_t)(n0 + nf * 8 + 2 * t + e) * K + g] = acc[0][nf][e];
+                    *reinterpret_cast<double2*>(mn + (size_t)g * NT + nf * 8 + 2 * t) = make_double2(acc[nf][0], acc[nf][1]);
             }
         }
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < NT * K; idx += SK_THREADS) {
-            const int n = idx / K, k = idx % K;
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < SK_WARPS; ++w) s += colpart[((size_t)w * KP + k) * NT + n];
-            cb.fvar[(size_t)(n0 + n) * K + k] = (variance - cb.asq[n0 + n]) + s;   // Knn - sum A^2 + sum LTA^2
-        }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[buf]);
     }
 }
 
 // ==================================================================================================
 // cond_bwd_a  (triangular route)
 //   Abar = sum_k Lq_k * (B_k diag(2 vbar_k))  +  q_mu * mubar^T  -  2 A diag(sum_k vbar_k)
-// from fvar = variance - |a|^2 + sum |b_k|^2, b_k = Lq_k^T a, fmean = a^T q_mu.  The right operand changes with k
-// (B_k tiles, re-staged K times per point tile), so each warp keeps the accumulators of ALL its row blocks
-// (NBW of them) in registers across the k loop.  Executed flops = algorithmic K M^2 (x17/16).
+// from fvar = variance - |a|^2 + sum |b_k|^2, b_k = Lq_k^T a, fmean = a^T q_mu.  The right operand changes with k:
+// per point tile the ring carries K + 1 stages (B_0 .. B_{K-1}, then A for the elementwise epilogue); each warp keeps
+// the accumulators of ALL its row blocks (NBW of them) in registers across the stages of a tile.
+// PROD_WARP: warp 8 feeds the ring; otherwise (accumulators too large for the 168-register cap of a 9-warp CTA: three
+// warps on one SM sub-partition) the producer duty rotates over the consumer warps: at the start of stage j, warp
+// j % 8 waits for every warp to leave stage j - 1 and refills that buffer with stage j + NBUF - 1.
 // ==================================================================================================
-template <int NT, int NBW>
-__global__ void __launch_bounds__(SK_THREADS) cond_bwd_a_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
+template <int NT, int NBUF, int NBW, bool PROD_WARP>
+__global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
+    cond_bwd_a_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
     constexpr int NF = NT / 8, STR = NT + 4;
     extern __shared__ __align__(16) double smem[];
     const int Mp = ly.Mp, K = ly.K;
-    // double-buffered right operand (B_k tiles) and per-tile adjoint slabs: the next (tile, k) operand streams in
-    // with cp.async while the current one is being multiplied
-    double* Tb = smem;                               // [2][Mp][STR]
-    double* mubTb = Tb + 2 * (size_t)Mp * STR;       // [2][KP][STR]  mubar^T (right operand of the q_mu segment)
-    double* vbb = mubTb + 2 * KP * STR;              // [2][KP][NT]   vbar^T
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* done = full + NBUF;
+    double* Tb = smem + SK_BAR_DOUBLES;                // [NBUF][Mp][STR]
+    double* mub = Tb + (size_t)NBUF * Mp * STR;        // [2][NT][K]  mubar slab of the tile (by tile parity)
+    double* vbs = mub + 2 * NT * KP;                   // [2][NT][K]  vbar slab
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nb16 = Mp / 16, C4 = Mp / 4;
-    const double sc_dummy[NF] = {};
-
-    for (int idx = threadIdx.x; idx < 2 * KP * STR + 2 * KP * NT; idx += SK_THREADS) mubTb[idx] = 0.0;   // k >= K rows stay 0
+    const size_t tile_elems = (size_t)Mp * STR;
+    const unsigned tile_bytes = (unsigned)(tile_elems * sizeof(double));
+    const unsigned slab_bytes = (unsigned)(NT * K * sizeof(double));
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], SK_WARPS); }
+        mbar_fence_init();
+    }
     __syncthreads();
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = my_tiles * (K + 1);
+    auto tile_of = [&](int ti) { return (int64_t)blockIdx.x + (int64_t)ti * gridDim.x; };
+    // stage j = (tile iteration ti, s): s < K -> B_s tile, s == K -> A tile.  One lane issues.
+    auto issue = [&](int j) {
+        const int ti = j / (K + 1), s = j - ti * (K + 1), buf = j % NBUF;
+        const int64_t tile = tile_of(ti);
+        if (j >= NBUF) mbar_wait(&done[buf], (unsigned)(((j / NBUF) - 1) & 1));
+        mbar_arrive_expect_tx(&full[buf], tile_bytes + (s == 0 ? 2 * slab_bytes : 0u));
+        const double* src = (s < K) ? cb.Bk + ((size_t)s * cb.tiles_cap + tile) * tile_elems : cb.A + (size_t)tile * tile_elems;
+        bulk_g2s(Tb + (size_t)buf * tile_elems, src, tile_bytes, &full[buf]);
+        if (s == 0) {
+            bulk_g2s(mub + (size_t)(ti & 1) * NT * KP, cb.mubar + (size_t)tile * NT * K, slab_bytes, &full[buf]);
+            bulk_g2s(vbs + (size_t)(ti & 1) * NT * KP, cb.vbar + (size_t)tile * NT * K, slab_bytes, &full[buf]);
+        }
+    };
+    if (PROD_WARP && warp == SK_WARPS) {
+        if (lane == 0)
+            for (int j = 0; j < total; ++j) issue(j);
+        return;
+    }
+    if (!PROD_WARP && warp == 0 && lane == 0)
+        for (int j = 0; j < NBUF && j < total; ++j) issue(j);
+
     const int nmy = my_block_count(warp, nb16);
-    auto seg_of = [&](int k, int i) {
-        const int b = snake_block(i, warp, nb16);
+    auto seg_of = [&](int k, int r) {
+        const int b = snake_block(r, warp, nb16);
         return Seg{ly.W_Lq + (size_t)k * Mp * Mp, 2 * b, 0};
     };
     WFrag wf;
     if (nmy > 0) wfrag_load(wf, seg_of(0, 0), C4, 0, lane);
-
-    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total = my_tiles * K;
-    auto issue = [&](int j) {   // stage operand j = (tile iteration, component) into buffer j & 1
-        const int ti = j / K, k = j - ti * K;
-        const int64_t n0 = (int64_t)(blockIdx.x + ti * gridDim.x) * NT;
-        load_tile_async<NT>(Tb + (size_t)(j & 1) * Mp * STR, cb.Bk + (size_t)k * Mp * cb.ldn, Mp, cb.ldn, n0);
-        if (k == 0) {
-            double* mT = mubTb + (size_t)(ti & 1) * KP * STR;
-            double* vT = vbb + (size_t)(ti & 1) * KP * NT;
-            for (int idx = threadIdx.x; idx < NT * K; idx += SK_THREADS) {
-                const int n = idx / K, kk = idx - n * K;
-                cp_async8(mT + kk * STR + n, cb.mubar + (size_t)(n0 + n) * K + kk);
-                cp_async8(vT + kk * NT + n, cb.vbar + (size_t)(n0 + n) * K + kk);
-            }
-            cp_async_commit();
-        }
-    };
-    if (total > 0) issue(0);
     double acc[NBW][2][NF][2];
     for (int j = 0; j < total; ++j) {
-        const int ti = j / K, k = j - ti * K;
-        const int64_t n0 = (int64_t)(blockIdx.x + ti * gridDim.x) * NT;
-        cp_async_wait<0>();    // operand j has landed ...
-        __syncthreads();       // ... for everyone, and every warp is done with operand j - 1
-        if (j + 1 < total) issue(j + 1);   // refill the buffer operand j - 1 used
-        const double* T = Tb + (size_t)(j & 1) * Mp * STR;
-        const double* mubT = mubTb + (size_t)(ti & 1) * KP * STR;
-        const double* vb = vbb + (size_t)(ti & 1) * KP * NT;
-        if (k == 0) {
+        const int ti = j / (K + 1), s = j - ti * (K + 1), buf = j % NBUF;
+        const double* T = Tb + (size_t)buf * tile_elems;
+        const double* mb = mub + (size_t)(ti & 1) * NT * KP;
+        const double* vb = vbs + (size_t)(ti & 1) * NT * KP;
+        if (!PROD_WARP && (j % SK_WARPS) == warp) {   // rotating producer duty: refill the buffer stage j - 1 used
+            const int jn = j + NBUF - 1;
+            if (jn >= NBUF && jn < total && lane == 0) issue(jn);
+            __syncwarp();
+        }
+        mbar_wait(&full[buf], (unsigned)((j / NBUF) & 1));
+        if (s == 0) {
 #pragma unroll
             for (int r = 0; r < NBW; ++r) zero_acc<NF>(acc[r]);
         }
-        // column weights 2 vbar_k of this lane's columns; applied once per (block, k) to the finished product
-        // Lq_k B_k instead of to every B fragment (keeps DMUL out of the DMMA loop)
-        double sc[NF][2];
+        if (s < K) {
+            // column weights 2 vbar_s of this lane's columns; applied once per (block, s) to the finished product
+            // Lq_s B_s instead of to every B fragment (keeps DMUL out of the DMMA loop)
+            double sc[NF][2];
 #pragma unroll
-        for (int nf = 0; nf < NF; ++nf) {
-            sc[nf][0] = 2.0 * vb[k * NT + nf * 8 + 2 * t];
-            sc[nf][1] = 2.0 * vb[k * NT + nf * 8 + 2 * t + 1];
-        }
+            for (int nf = 0; nf < NF; ++nf) {
+                sc[nf][0] = 2.0 * vb[(nf * 8 + 2 * t) * K + s];
+                sc[nf][1] = 2.0 * vb[(nf * 8 + 2 * t + 1) * K + s];
+            }
 #pragma unroll
-        for (int r = 0; r < NBW; ++r) {
-            if (r >= nmy) continue;
-            const int b = snake_block(r, warp, nb16);
-            double ck[2][NF][2];
-            zero_acc<NF>(ck);
-            const Seg nxt = (r + 1 < nmy) ? seg_of(k, r + 1) : seg_of(k + 1 < K ? k + 1 : 0, 0);
-            wgemm_seg<NT>(seg_of(k, r), (b + 1) * 4, C4, T, ck, lane, wf, nxt);   // lower triangular
+            for (int r = 0; r < NBW; ++r) {
+                if (r >= nmy) continue;
+                const int b = snake_block(r, warp, nb16);
+                double ck[2][NF][2];
+                zero_acc<NF>(ck);
+                const Seg nxt = (r + 1 < nmy) ? seg_of(s, r + 1) : seg_of(s + 1 < K ? s + 1 : 0, 0);
+                wgemm_seg<NT>(seg_of(s, r), (b + 1) * 4, C4, T, ck, lane, wf, nxt);   // lower triangular
 #pragma unroll
-            for (int mf = 0; mf < 2; ++mf)
+                for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
-                for (int nf = 0; nf < NF; ++nf) {
-                    acc[r][mf][nf][0] = fma(ck[mf][nf][0], sc[nf][0], acc[r][mf][nf][0]);
-                    acc[r][mf][nf][1] = fma(ck[mf][nf][1], sc[nf][1], acc[r][mf][nf][1]);
-                }
-        }
-        if (k == K - 1) {   // tile epilogue: + q_mu mubar^T - 2 A diag(sum_k vbar_k), in place over A
+                    for (int nf = 0; nf < NF; ++nf) {
+                        acc[r][mf][nf][0] = fma(ck[mf][nf][0], sc[nf][0], acc[r][mf][nf][0]);
+                        acc[r][mf][nf][1] = fma(ck[mf][nf][1], sc[nf][1], acc[r][mf][nf][1]);
+                    }
+            }
+        } else {   // tile epilogue: + q_mu mubar^T - 2 A diag(sum_k vbar_k), written over A (tile-major, in place)
+            double* Aout = cb.A + (size_t)tile_of(ti) * tile_elems;
             double vs[NF][2];
 #pragma unroll
             for (int nf = 0; nf < NF; ++nf) {
                 vs[nf][0] = vs[nf][1] = 0.0;
                 for (int kk = 0; kk < K; ++kk) {
-                    vs[nf][0] += vb[kk * NT + nf * 8 + 2 * t];
-                    vs[nf][1] += vb[kk * NT + nf * 8 + 2 * t + 1];
+                    vs[nf][0] += vb[(nf * 8 + 2 * t) * K + kk];
+                    vs[nf][1] += vb[(nf * 8 + 2 * t + 1) * K + kk];
                 }
             }
+            // B fragments of mubar^T [KP x NT]: element (k = kb*4 + t, n = nf*8 + g)
+            double bm[KP / 4][NF];
+#pragma unroll
+            for (int kb = 0; kb < KP / 4; ++kb)
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) bm[kb][nf] = (kb * 4 + t < K) ? mb[(nf * 8 + g) * K + kb * 4 + t] : 0.0;
 #pragma unroll
             for (int r = 0; r < NBW; ++r) {
                 const int b = snake_block(r, warp, nb16);
-                if (b < 0) continue;
-                wgemm_block<NT, false>(ly.W_m, KP / 4, 2 * b, 0, KP / 4, mubT, acc[r], sc_dummy, lane);
+                if (r >= nmy || b < 0) continue;
+#pragma unroll
+                for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+                    for (int kb = 0; kb < KP / 4; ++kb) {
+                        const double a = __ldg(ly.W_m + ((size_t)(2 * b + mf) * (KP / 4) + kb) * 32 + lane);
+#pragma unroll
+                        for (int nf = 0; nf < NF; ++nf) dmma(acc[r][mf][nf], a, bm[kb][nf]);
+                    }
 #pragma unroll
                 for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
                     for (int nf = 0; nf < NF; ++nf) {
-                        double2* p = reinterpret_cast<double2*>(cb.A + (size_t)(b * 16 + mf * 8 + g) * cb.ldn + n0 + nf * 8 + 2 * t);
-                        const double2 av = *p;
-                        *p = make_double2(acc[r][mf][nf][0] - 2.0 * vs[nf][0] * av.x, acc[r][mf][nf][1] - 2.0 * vs[nf][1] * av.y);
+                        const size_t off = (size_t)(b * 16 + mf * 8 + g) * STR + nf * 8 + 2 * t;
+                        const double2 av = *reinterpret_cast<const double2*>(T + off);
+                        *reinterpret_cast<double2*>(Aout + off) =
+                            make_double2(acc[r][mf][nf][0] - 2.0 * vs[nf][0] * av.x, acc[r][mf][nf][1] - 2.0 * vs[nf][1] * av.y);
                     }
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[buf]);
     }
 }
 
 // ==================================================================================================
-// cond_bwd_b
+// cond_bwd_b :  Kuf_bar = L^-T Abar ; E = Kuf_bar .* Kuf ; per-row sums of E [1, xs_d, xs_d^2]
+// Two CTAs per SM (16 warps), like cond_fwd_a: the per-fragment epilogue regenerates Kuf (exp) and is scalar FP64
+// work that overlaps best with many DMMA warps.  The Abar tile arrives by one cp.async.bulk on an mbarrier.
 // ==================================================================================================
 template <int NT>
-__global__ void __launch_bounds__(SK_THREADS) cond_bwd_b_kernel(LayerDev ly, ChunkBuffers cb, int ntiles,
+__global__ void __launch_bounds__(SK_CTHREADS) cond_bwd_b_kernel(LayerDev ly, ChunkBuffers cb, int ntiles,
                                                                 double* esum_part) {
     constexpr int NF = NT / 8, STR = NT + 4;
     extern __shared__ __align__(16) double smem[];
     const int Mp = ly.Mp, Dp = ly.Dp, D = ly.D, XSTR = xs_stride(Dp), E = 1 + 2 * Dp;
-    double* T = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    double* T = smem + SK_BAR_DOUBLES;
     double* Xs = T + (size_t)Mp * STR;
     double* xs2 = Xs + NT * XSTR;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nb16 = Mp / 16, C4 = Mp / 4;
+    const size_t tile_elems = (size_t)Mp * STR;
+    const unsigned tile_bytes = (unsigned)(tile_elems * sizeof(double));
     const double variance = ly.variance[0];
     double* my_part = esum_part + (size_t)blockIdx.x * Mp * E;
     const int nmy = my_block_count(warp, nb16);
     auto seg_of = [&](int i) { const int b = snake_block(i, warp, nb16); return Seg{ly.W_LinvT, 2 * b, 4 * b}; };
     WFrag wf;
     if (nmy > 0) wfrag_load(wf, seg_of(0), C4, seg_of(0).kb0, lane);
+    if (threadIdx.x == 0) { mbar_init(full, 1); mbar_fence_init(); }
+    __syncthreads();
 
+    unsigned phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t n0 = (int64_t)tile * NT;
-        load_tile_async<NT>(T, cb.A, Mp, cb.ldn, n0);
-        stage_x<NT>(ly, cb, n0, Xs, xs2);
-        cp_async_wait<0>();
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(full, tile_bytes);
+            bulk_g2s(T, cb.A + (size_t)tile * tile_elems, tile_bytes, full);
+        }
+        if (warp == 1) stage_x_warp<NT>(ly, cb, n0, Xs, xs2, lane);
         __syncthreads();
+        mbar_wait(full, phase);
+        phase ^= 1u;
         for (int i = 0; i < nmy; ++i) {
             const int b = snake_block(i, warp, nb16);
             double acc[2][NF][2];
@@ -552,7 +581,7 @@ __global__ void __launch_bounds__(SK_THREADS) cond_bwd_b_kernel(LayerDev ly, Chu
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();   // everyone is done with T and Xs before the next tile overwrites them
     }
 }
 
@@ -561,20 +590,45 @@ __global__ void __launch_bounds__(SK_THREADS) cond_bwd_b_kernel(LayerDev ly, Chu
 // ==================================================================================================
 int stream_max_parts(const Launch& ln) { return ln.num_sms * 4; }
 
-static int pick_nt(int Mp, size_t extra_bytes_nt32) {
-    // widest supported tile whose [Mp x (NT+4)] operand fits in 227 KB (Mp=256, NT=32: 74 KB -> 3 CTAs/SM)
+// Tile width of a layer's tile-major workspace (all four kernels and the SYRK share it) and the ring depth:
+//   NT = 32, 2 buffers  while two [Mp x 36] tiles fit next to the per-kernel extras;
+//   NT = 16, 2 buffers  up to Mp = 672;  NT = 16, 1 buffer beyond (no load / multiply overlap inside a CTA).
+static size_t extras_bytes(int Mp, int Dp, int K, int nt) {
+    const size_t fa = (size_t)(nt * xs_stride(Dp) + nt) * 8;
+    const size_t fb = (size_t)2 * 2 * SK_WARPS * K * nt * 8;
+    const size_t ba = (size_t)4 * nt * KP * 8;
+    const size_t bb = (size_t)2 * (nt * xs_stride(Dp) + nt) * 8;
+    size_t m = fa;
+    if (fb > m) m = fb;
+    if (ba > m) m = ba;
+    if (bb > m) m = bb;
+    (void)Mp;
+    return m + SK_BAR_DOUBLES * 8;
+}
+int layer_tile_width(int Mp, int Dp, int K) {
     const size_t cap = 227 * 1024;
-    if ((size_t)Mp * 36 * 8 + extra_bytes_nt32 <= cap) return 32;
-    if ((size_t)Mp * 20 * 8 + extra_bytes_nt32 <= cap) return 16;
-    return 0;
+    return (2 * (size_t)Mp * 36 * 8 + extras_bytes(Mp, Dp, K, 32) <= cap) ? 32 : 16;
+}
+static int ring_depth(int Mp, int Dp, int K, int nt) {
+    return (2 * (size_t)Mp * (nt + 4) * 8 + extras_bytes(Mp, Dp, K, nt) <= (size_t)227 * 1024) ? 2 : 1;
 }
 
 template <typename KernelT>
-static int persistent_grid(KernelT kernel, size_t smem, int ntiles, int cap, const Launch& ln) {
+static int persistent_grid(KernelT kernel, int threads, size_t smem, int ntiles, int cap, const Launch& ln) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    (void)threads;
+    int grid = ln.num_sms;
+    if (grid > ntiles) grid = ntiles;
+    if (cap > 0 && grid > cap) grid = cap;
+    return grid < 1 ? 1 : grid;
+}
+// grid = SMs x resident CTAs (occupancy query) for the kernels that run several CTAs per SM
+template <typename KernelT>
+static int occupancy_grid(KernelT kernel, int threads, size_t smem, int ntiles, int cap, const Launch& ln) {
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, SK_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
     if (occ < 1) occ = 1;
     int grid = ln.num_sms * occ;
     if (grid > ntiles) grid = ntiles;
@@ -583,67 +637,67 @@ static int persistent_grid(KernelT kernel, size_t smem, int ntiles, int cap, con
 }
 
 void cond_fwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
-    const int XSTR = xs_stride(ly.Dp);
-    const int nt = pick_nt(ly.Mp, (size_t)(32 * XSTR + 32 + SK_WARPS * 32) * 8);
-    auto launch = [&](auto kernel, int NT) {
-        const size_t smem = ((size_t)ly.Mp * (NT + 4) + NT * XSTR + NT + SK_WARPS * NT) * sizeof(double);
-        const int ntiles = (int)((cb.n + NT - 1) / NT);
-        const int grid = persistent_grid(kernel, smem, ntiles, 0, ln);
-        kernel<<<grid, SK_THREADS, smem, ln.stream>>>(ly, cb, ntiles);
+    const int NT = cb.tw;
+    const size_t smem = ((size_t)ly.Mp * (NT + 4) + NT * xs_stride(ly.Dp) + NT) * sizeof(double);
+    const int ntiles = (int)((cb.n + NT - 1) / NT);
+    auto launch = [&](auto kernel) {
+        const int grid = occupancy_grid(kernel, SK_CTHREADS, smem, ntiles, 0, ln);
+        kernel<<<grid, SK_CTHREADS, smem, ln.stream>>>(ly, cb, ntiles);
         ln.tick();
     };
-    if (nt == 32) launch(cond_fwd_a_kernel<32>, 32); else launch(cond_fwd_a_kernel<16>, 16);
+    if (NT == 32) launch(cond_fwd_a_kernel<32>); else launch(cond_fwd_a_kernel<16>);
 }
 
 void cond_fwd_b(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
-    const int nt = pick_nt(ly.Mp, (size_t)(SK_WARPS * KP * 32) * 8);
-    auto launch = [&](auto kernel, int NT) {
-        const size_t smem = ((size_t)ly.Mp * (NT + 4) + (size_t)SK_WARPS * KP * NT) * sizeof(double);
-        const int ntiles = (int)((cb.n + NT - 1) / NT);
-        const int grid = persistent_grid(kernel, smem, ntiles, 0, ln);
-        kernel<<<grid, SK_THREADS, smem, ln.stream>>>(ly, cb, ntiles);
+    const int NT = cb.tw, nbuf = ring_depth(ly.Mp, ly.Dp, ly.K, NT);
+    const int threads = SK_CTHREADS + 32;
+    const size_t smem = ((size_t)SK_BAR_DOUBLES + (size_t)nbuf * ly.Mp * (NT + 4) + (size_t)2 * nbuf * SK_WARPS * ly.K * NT) * sizeof(double);
+    const int ntiles = (int)((cb.n + NT - 1) / NT);
+    auto launch = [&](auto kernel) {
+        const int grid = persistent_grid(kernel, threads, smem, ntiles, 0, ln);
+        kernel<<<grid, threads, smem, ln.stream>>>(ly, cb, ntiles);
         ln.tick();
     };
-    if (nt == 32) launch(cond_fwd_b_kernel<32>, 32); else launch(cond_fwd_b_kernel<16>, 16);
+    if (NT == 32) launch(cond_fwd_b_kernel<32, 2>);
+    else if (nbuf == 2) launch(cond_fwd_b_kernel<16, 2>);
+    else launch(cond_fwd_b_kernel<16, 1>);
 }
 
 void cond_bwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
-    // double-buffered operand: two [Mp x (NT+4)] tiles must fit
-    int nt = 0;
-    if (2 * ((size_t)ly.Mp * 36 + KP * 36 + KP * 32) * 8 <= 227 * 1024) nt = 32;
-    else if (2 * ((size_t)ly.Mp * 20 + KP * 20 + KP * 16) * 8 <= 227 * 1024) nt = 16;
+    const int NT = cb.tw, nbuf = ring_depth(ly.Mp, ly.Dp, ly.K, NT);
     const int nbw = (ly.Mp / 16 + SK_WARPS - 1) / SK_WARPS;   // 16-row blocks per warp
-    auto launch = [&](auto kernel, int NT) {
-        const size_t smem = 2 * ((size_t)ly.Mp * (NT + 4) + KP * (NT + 4) + KP * NT) * sizeof(double);
-        const int ntiles = (int)((cb.n + NT - 1) / NT);
-        const int grid = persistent_grid(kernel, smem, ntiles, 0, ln);
-        kernel<<<grid, SK_THREADS, smem, ln.stream>>>(ly, cb, ntiles);
+    const size_t smem = ((size_t)SK_BAR_DOUBLES + (size_t)nbuf * ly.Mp * (NT + 4) + (size_t)4 * NT * KP) * sizeof(double);
+    const int ntiles = (int)((cb.n + NT - 1) / NT);
+    auto launch = [&](auto kernel, int threads) {
+        const int grid = persistent_grid(kernel, threads, smem, ntiles, 0, ln);
+        kernel<<<grid, threads, smem, ln.stream>>>(ly, cb, ntiles);
         ln.tick();
     };
-    if (nt == 32 && nbw <= 4) {   // accumulators of all row blocks live in registers: NBW*2*NF*2 doubles per lane
-        if (nbw <= 1) launch(cond_bwd_a_kernel<32, 1>, 32);
-        else if (nbw <= 2) launch(cond_bwd_a_kernel<32, 2>, 32);
-        else launch(cond_bwd_a_kernel<32, 4>, 32);
+    // accumulators of all row blocks live in registers: NBW * 2 * NF * 2 doubles per lane
+    if (NT == 32) {
+        if (nbw <= 1) launch(cond_bwd_a_kernel<32, 2, 1, true>, SK_CTHREADS + 32);
+        else launch(cond_bwd_a_kernel<32, 2, 2, false>, SK_CTHREADS);
+    } else if (nbuf == 2) {
+        if (nbw <= 4) launch(cond_bwd_a_kernel<16, 2, 4, true>, SK_CTHREADS + 32);
+        else launch(cond_bwd_a_kernel<16, 2, 6, false>, SK_CTHREADS);
     } else {
-        if (nbw <= 4) launch(cond_bwd_a_kernel<16, 4>, 16);
-        else if (nbw <= 8) launch(cond_bwd_a_kernel<16, 8>, 16);
-        else launch(cond_bwd_a_kernel<16, 11>, 16);
+        if (nbw <= 8) launch(cond_bwd_a_kernel<16, 1, 8, false>, SK_CTHREADS);
+        else launch(cond_bwd_a_kernel<16, 1, 11, false>, SK_CTHREADS);
     }
 }
 
 void cond_bwd_b(const LayerDev& ly, const ChunkBuffers& cb, double* esum_part, int nparts_cap, int* nparts,
                 const Launch& ln) {
-    const int XSTR = xs_stride(ly.Dp);
-    const int nt = pick_nt(ly.Mp, (size_t)(32 * XSTR + 32) * 8);
-    auto launch = [&](auto kernel, int NT) {
-        const size_t smem = ((size_t)ly.Mp * (NT + 4) + NT * XSTR + NT) * sizeof(double);
-        const int ntiles = (int)((cb.n + NT - 1) / NT);
-        const int grid = persistent_grid(kernel, smem, ntiles, nparts_cap, ln);
-        kernel<<<grid, SK_THREADS, smem, ln.stream>>>(ly, cb, ntiles, esum_part);
+    const int NT = cb.tw;
+    const size_t smem = ((size_t)SK_BAR_DOUBLES + (size_t)ly.Mp * (NT + 4) + NT * xs_stride(ly.Dp) + NT) * sizeof(double);
+    const int ntiles = (int)((cb.n + NT - 1) / NT);
+    auto launch = [&](auto kernel) {
+        const int grid = occupancy_grid(kernel, SK_CTHREADS, smem, ntiles, nparts_cap, ln);
+        kernel<<<grid, SK_CTHREADS, smem, ln.stream>>>(ly, cb, ntiles, esum_part);
         ln.tick();
         if (grid > *nparts) *nparts = grid;
     };
-    if (nt == 32) launch(cond_bwd_b_kernel<32>, 32); else launch(cond_bwd_b_kernel<16>, 16);
+    if (NT == 32) launch(cond_bwd_b_kernel<32>); else launch(cond_bwd_b_kernel<16>);
 }
 
 }  // namespace mgp

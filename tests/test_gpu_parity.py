@@ -134,7 +134,13 @@ def _synthetic_case(N, D, M, K, S, seed, model="SMGP", ls_assign=1.1):
     return case, X, Y, z, u
 
 
-@pytest.mark.parametrize("N,D,M,K,S", [(3000, 2, 256, 4, 16), (700, 8, 96, 8, 8), (257, 1, 40, 3, 5)])
+@pytest.mark.parametrize("N,D,M,K,S", [(3000, 2, 256, 4, 16), (700, 8, 96, 8, 8), (257, 1, 40, 3, 5),
+                                       # every tile-width / ring-depth / accumulator variant of the streaming kernels:
+                                       (150, 2, 324, 4, 4),     # NT 32, 3 row blocks per warp
+                                       (210, 3, 480, 3, 4),     # NT 16, 2-deep ring, producer warp
+                                       (130, 8, 640, 5, 3),     # NT 16, 2-deep ring, rotating producer duty
+                                       (300, 8, 1024, 8, 4),    # BASELINE config #5's M, K: NT 16, single buffer
+                                       (90, 4, 1200, 2, 3)])    # largest accumulator variant
 def test_oracle_sized_synthetic_vs_oracle(N, D, M, K, S, hg):
     """BASELINE config #4 / #5 shapes at an N the CPU oracle finishes in seconds; ragged N on purpose."""
     from oracle import svgp_mixture as O

@@ -193,6 +193,9 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; rank 0's stdout must stay ONE JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -298,13 +301,26 @@ def main():
         # reduction, which this design folds into the S_k algebra); x2 layers)
         alg = {"cond_fwd_a": 2 * M * M, "cond_fwd_b": 2 * K * M * M, "syrk": 2 * K * M * M, "cond_bwd_a": 2 * K * M * M,
                "cond_bwd_b": 2 * 2 * M * M}
-        executed = {"cond_fwd_a": 2 * M * M * 17 / 16, "cond_fwd_b": 2 * K * M * M * 17 / 16, "syrk": 2 * K * M * M * 40960 / 32896,
-                    "cond_bwd_a": 2 * 2 * K * M * M, "cond_bwd_b": 2 * M * M * 17 / 16}
+        # executed = algorithmic x the padding of the triangular blocking (16-row blocks: 17/16; SYRK: 528 computed
+        # 8x8 fragments for 514 algorithmic ones)
+        executed = {"cond_fwd_a": 2 * M * M * 17 / 16, "cond_fwd_b": 2 * K * M * M * 17 / 16, "syrk": 2 * K * M * M * 528 / 514,
+                    "cond_bwd_a": 2 * K * M * M * 17 / 16, "cond_bwd_b": 2 * M * M * 17 / 16}
         dom = max(alg, key=lambda k: per_stage.get(k, 0.0))
         dom_ms = per_stage[dom]
         achieved = alg[dom] * n_local / (dom_ms * 1e-3) / 1e12
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel from the committed `ncu --set full`
+        # capture of this command at 1 GPU (profiles/r01_kernel_traffic.json); scaled by the shard size
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")))
+            if dom in tj["per_launch_dram_bytes"]:
+                traffic = tj["per_launch_dram_bytes"][dom] * n_local / tj["points_per_launch"]
+        except (OSError, KeyError, ValueError):
+            traffic = None
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                    "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                    "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
+                    "launches_per_step": 2, "alg_flops_per_launch": alg[dom] * n_local / 2,
+                    "all_kernels_tflops": {k: alg[k] * n_local / (per_stage[k] * 1e-3) / 1e12 for k in alg if per_stage.get(k)},
                     "executed_tflops": executed[dom] * n_local / (dom_ms * 1e-3) / 1e12,
                     "peak_source": "FP64 DMMA issue-rate peak measured on this pool's B200 by tools/fp64_peak.cu "
                                    "(profiles/r01_fp64_peak_microbench.txt); MEASURED_PEAKS.json has no FP64 entry; "

@@ -48,7 +48,7 @@ def main():
         if gap > 0:
             total_gap += gap
         dur = e.time_range.end - e.time_range.start
-        if dur > 2000 or gap > 100:
+        if dur > 2000 or gap > 100 or os.environ.get('GAP_ALL'):
             print(f"{(e.time_range.start - t0) / 1e3:9.3f} ms  dur {dur / 1e3:8.3f} ms  gap {gap / 1e3:7.3f} ms  {e.name[:70]}")
         prev_end = max(prev_end, e.time_range.end)
     print(f"span {(prev_end - t0) / 1e3:.3f} ms, idle gaps {total_gap / 1e3:.3f} ms, kernels {len(evs)}")

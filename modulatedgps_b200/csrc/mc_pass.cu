@@ -364,20 +364,18 @@ void mc_pass(const McArgs& a, double* block_part, const Launch& ln) {
     ln.tick();
 }
 
-// header[0..19) += sum over blocks (single block, fixed order)
+// header[q] += sum over blocks, one CTA per entry q (fixed order => deterministic)
 __global__ void __launch_bounds__(256) mc_fold_kernel(const double* block_part, int nblocks, double* hdr) {
     __shared__ double red[32];
-    for (int q = 0; q < MC_NPART - 1; ++q) {
-        double s = 0.0;
-        for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += block_part[(size_t)b * MC_NPART + q];
-        s = block_sum(s, red);
-        if (threadIdx.x == 0) hdr[q] += s;
-        __syncthreads();
-    }
+    const int q = blockIdx.x;
+    double s = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) s += block_part[(size_t)b * MC_NPART + q];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) hdr[q] += s;
 }
 
 void mc_fold(const double* block_part, int nblocks, double* rb_header, const Launch& ln) {
-    mc_fold_kernel<<<1, 256, 0, ln.stream>>>(block_part, nblocks, rb_header);
+    mc_fold_kernel<<<MC_NPART - 1, 256, 0, ln.stream>>>(block_part, nblocks, rb_header);
     ln.tick();
 }
 

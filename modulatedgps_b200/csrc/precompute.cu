@@ -400,43 +400,41 @@ __global__ void __launch_bounds__(128) kuu_bwd_kernel(LayerDev ly, const double*
 }
 
 // gauss_kl (whitened): 0.5 [ sum q_mu^2 - M K - sum log diag(Lq)^2 + sum Lq^2 ]
-// stage 1: one CTA per component k sums its Lq_k terms (block K: the q_mu term); stage 2: fixed-order total.
-__global__ void __launch_bounds__(256) kl_part_kernel(LayerDev ly, double* part) {
+// stage 1: CTA (k, c) sums the terms of rows i = c mod KL_NC of Lq_k (k == K: the q_mu term); stage 2: fixed-order total.
+constexpr int KL_NC = 4;
+__global__ void __launch_bounds__(1024) kl_part_kernel(LayerDev ly, double* part) {
     __shared__ double red[32];
-    const int M = ly.M, Mp = ly.Mp, K = ly.K, k = blockIdx.x;
+    const int M = ly.M, Mp = ly.Mp, K = ly.K, k = blockIdx.x, c = blockIdx.y;
     double s = 0.0;
     if (k < K) {
         const double* Lq = ly.Lq_rm + (size_t)k * Mp * Mp;
-        for (int idx = threadIdx.x; idx < M * Mp; idx += blockDim.x) {
-            const int i = idx / Mp, j = idx - i * Mp;
-            if (j <= i) {
-                const double v = Lq[idx];
+        for (int i = c; i < M; i += KL_NC)
+            for (int j = threadIdx.x; j <= i; j += blockDim.x) {
+                const double v = Lq[(size_t)i * Mp + j];
                 s += v * v;
                 if (i == j) s -= log(v * v);
             }
-        }
     } else {
-        for (int idx = threadIdx.x; idx < M * K; idx += blockDim.x) {
+        for (int idx = c * blockDim.x + threadIdx.x; idx < M * K; idx += KL_NC * blockDim.x) {
             const double v = ly.q_mu[idx];
             s += v * v;
         }
     }
     s = block_sum(s, red);
-    if (threadIdx.x == 0) part[k] = s;
+    if (threadIdx.x == 0) part[k * KL_NC + c] = s;
 }
 
 __global__ void kl_total_kernel(LayerDev ly, const double* part, double* kl_out) {
     if (threadIdx.x == 0) {
         double s = 0.0;
-        for (int k = 0; k <= ly.K; ++k) s += part[k];
+        for (int k = 0; k < (ly.K + 1) * KL_NC; ++k) s += part[k];
         kl_out[0] = 0.5 * (s - (double)ly.M * (double)ly.K);
     }
 }
 
 static void kl_launch(const LayerDev& ly, double* kl_out, const Launch& ln) {
-    // rowout doubles as the [K + 1] partial buffer when it exists; Kuu's padding rows are free otherwise
-    double* part = ly.zs2 + ly.Mp;   // zs2 is allocated with 2 * Mp doubles (api.cu); second half = scratch
-    kl_part_kernel<<<ly.K + 1, 256, 0, ln.stream>>>(ly, part);
+    double* part = ly.zs2 + ly.Mp;   // zs2 is allocated with 2 * Mp + 16 doubles (api.cu); second half = scratch (>= 36)
+    kl_part_kernel<<<dim3(ly.K + 1, KL_NC), 1024, 0, ln.stream>>>(ly, part);
     kl_total_kernel<<<1, 32, 0, ln.stream>>>(ly, part, kl_out);
     ln.tick(2);
 }

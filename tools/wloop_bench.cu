@@ -143,6 +143,63 @@ __global__ void wloop_pp(const double* W, int Mp, int nmat, int iters, double* o
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// simple loop + one prefetch.global.L1 instruction per group, PD groups ahead (16 lanes cover the 16 lines of a group)
+template <int NT, int PD>
+__global__ void wloop_pf(const double* W, int Mp, int nmat, int iters, double* out) {
+    constexpr int NF = NT / 8, STR = NT + 4;
+    extern __shared__ double T[];
+    for (int i = threadIdx.x; i < Mp * STR; i += blockDim.x) T[i] = 1e-3 * (i % 13);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5, g = lane >> 2, t = lane & 3;
+    const int nb16 = Mp / 16, C4 = Mp / 4;
+    const double* tb = T + t * STR + g;
+    double acc[2][NF][2];
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+    WFrag f, n;
+    int b = warp % nb16, m = 0;
+    wfrag_load(f, W, 2 * b, C4, 0, lane);
+    for (int it = 0; it < iters; ++it) {
+        const double* w = W + (size_t)m * Mp * Mp;
+        int nb = b + nw; int nm = m;
+        if (nb >= nb16) { nb -= nb16; nm = (m + 1) % nmat; }
+        const double* wn = W + (size_t)nm * Mp * Mp;
+        for (int kb = 0; kb < C4; kb += 4) {
+            {   // prefetch group kb + 4 * PD of this row block (wraps into the next block's start: good enough for a ceiling test)
+                int pk = kb + 4 * PD;
+                const double* pw = w; int pb = b;
+                if (pk >= C4) { pk -= C4; pw = wn; pb = nb; }
+                if (lane < 16) {
+                    const double* a = pw + ((size_t)(2 * pb + (lane >> 3)) * C4 + pk) * 32 + (lane & 7) * 16;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+                }
+            }
+            if (kb + 4 < C4) wfrag_load(n, w, 2 * b, C4, kb + 4, lane);
+            else wfrag_load(n, wn, 2 * nb, C4, 0, lane);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double* tr = tb + (size_t)(kb + j) * 4 * STR;
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) {
+                    const double bb = tr[nf * 8];
+                    dmma(acc[0][nf], f.a0[j], bb);
+                    dmma(acc[1][nf], f.a1[j], bb);
+                }
+            }
+            f = n;
+        }
+        b = nb; m = nm;
+    }
+    double s = 0;
+#pragma unroll
+    for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) s += acc[mf][nf][0] + acc[mf][nf][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main() {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
     const int nsm = p.multiProcessorCount, Mp = 256, nmat = 4;
@@ -187,6 +244,10 @@ int main() {
     run(wloop_pp<32, 1>, 32, 1, 256);
     run(wloop_pp<32, 2>, 32, 1, 512, 2);
     run(wloop_pp<32, 1>, 32, 2, 256);
+    printf("simple loop + prefetch.global.L1 PD groups ahead, 8 warps:\n");
+    run(wloop_pf<32, 2>, 32, 1, 256);
+    run(wloop_pf<32, 3>, 32, 1, 256);
+    run(wloop_pf<32, 4>, 32, 1, 256);
     fill(true);
     printf("same with random W (data-dependent power / clocks?):\n");
     run(wloop_pp<32, 1>, 32, 1, 256);

@@ -122,6 +122,16 @@ int mgp_predict_samples(mgp_ctx* ctx, const mgp_layer* pred, const mgp_layer* as
                         const double* lik_var, const double* X, int64_t N, int32_t S, double temperature,
                         const mgp_noise* noise, const double* z_pred, double* samples_y, double* samples_f);
 
+/* SMGP.W_dist(X).sample(1)[0] reshaped [S, N, K] — models.py:55-61,73-74: relaxed one-hot (Gumbel-softmax at
+ * `temperature`) sample of the assign layer's reparameterised logits.  noise as in mgp_elbo_local. */
+int mgp_w_sample(mgp_ctx* ctx, const mgp_layer* assign, const double* X, int64_t N, int32_t S, double temperature,
+                 const mgp_noise* noise, double* W);
+
+/* SMGP.E_log_p_Y(X, Y, W_SND) — models.py:63-67: out [N] = logsumexp_S(sum_k W ve) - log S with the expert
+ * likelihood's variational expectation ve (likelihoods.py:39-41 / gpflow MultiClass).  W [S, N, K]. */
+int mgp_e_log_p_y(mgp_ctx* ctx, const mgp_layer* pred, int32_t lik, const double* lik_var, const double* X,
+                  const double* Y, int64_t N, int32_t S, const double* W, double* out);
+
 /* Size (in doubles) of the flat reduction buffer of mgp_elbo_local for these layers. */
 int64_t mgp_reduce_buffer_len(const mgp_layer* pred, const mgp_layer* assign);
 
@@ -149,6 +159,38 @@ int mgp_elbo_fwd_bwd(mgp_ctx* ctx, const mgp_elbo_cfg* cfg, const mgp_layer* pre
                      const double* X, const double* Y, int64_t N_local, const mgp_noise* noise,
                      double* elbo, mgp_layer_grad* pred_grad, mgp_layer_grad* assign_grad,
                      double* lik_var_grad, double* assign_lik_var_grad);
+
+/* ---- the callers either side of the ELBO step, stream-ordered, no ctx needed ---------- */
+#define MGP_TRANSFORM_IDENTITY 0
+#define MGP_TRANSFORM_SOFTPLUS 1      /* gpflow positive(): d constrained / d theta = sigmoid(theta) */
+#define MGP_ADAM_MAX_SLOTS 16
+typedef struct {
+    double* theta;          /* [n] unconstrained variable, updated in place */
+    const double* grad;     /* d ELBO / d CONSTRAINED value as mgp_elbo_finish wrote it */
+    double* m;              /* [n] first moment */
+    double* v;              /* [n] second moment */
+    const int64_t* gather;  /* NULL, or [n] positions in `grad` (fill-triangular: vector entry i <- tril entry gather[i]) */
+    int64_t n;
+    int32_t transform;      /* MGP_TRANSFORM_* */
+    int32_t reserved;
+} mgp_adam_slot;
+
+/* One fused Adam update of every trainable variable — replaces tf.optimizers.Adam(lr).minimize(training_loss,
+ * model.trainable_variables) of utils/training_utils.py:6-10, TF 2.10 Keras defaults beta1 .9, beta2 .999, eps 1e-7.
+ * grad_scale = -1 turns ELBO gradients into gradients of the training loss (models.py:81-83).  step >= 1. */
+int mgp_adam_step(void* cuda_stream, const mgp_adam_slot* slots, int32_t nslots, double grad_scale, double lr,
+                  double beta1, double beta2, double eps, int64_t step);
+
+/* Minibatch gather: Xb[r] = X[idx[r]], Yb[r] = Y[idx[r]] — the device half of
+ * tf.data.Dataset.from_tensor_slices((X, Y)).shuffle(N).batch(B).repeat() (demos/demo_tf2.py:53-56). */
+int mgp_gather_rows(void* cuda_stream, const double* X, const double* Y, const int64_t* idx, int64_t B, int32_t D,
+                    double* Xb, double* Yb);
+
+/* `iters` Lloyd iterations from the given centroids [M, D] (in place), then labels int32 [N], cluster sizes int32 [M]
+ * and the mean Euclidean distance to the nearest centroid (scipy.cluster.vq.kmeans' distortion; call site
+ * demos/demo_tf2.py:39).  scratch: >= 592 doubles.  Empty clusters keep their centroid and report count 0. */
+int mgp_kmeans_iterate(void* cuda_stream, const double* X, int64_t N, int32_t D, double* centroids, int32_t M,
+                       int32_t iters, int32_t* label, int32_t* count, double* scratch, double* distortion);
 
 /* Stage-level entry points (used by the parity tests to localise a failure; same kernels as above).
  * L, Linv: [M, M] row-major lower-triangular outputs for one layer. */

@@ -41,6 +41,15 @@ class MgpElboCfg(C.Structure):
                 ("temperature", C.c_double), ("num_data", C.c_double), ("n_global", C.c_int64)]
 
 
+class MgpAdamSlot(C.Structure):
+    _fields_ = [("theta", C.c_void_p), ("grad", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("gather", C.c_void_p),
+                ("n", C.c_int64), ("transform", C.c_int32), ("reserved", C.c_int32)]
+
+
+TRANSFORM_IDENTITY, TRANSFORM_SOFTPLUS = 0, 1
+ADAM_MAX_SLOTS = 16
+
+
 class MgpError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"libmgp error {code}: {message}")
@@ -73,6 +82,10 @@ _PROTOTYPES = {
     "mgp_predict_samples": (C.c_int, [C.c_void_p, C.POINTER(MgpLayer), C.POINTER(MgpLayer), C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.POINTER(MgpNoise), C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "mgp_w_sample": (C.c_int, [C.c_void_p, C.POINTER(MgpLayer), C.c_void_p, C.c_int64, C.c_int32, C.c_double,
+                               C.POINTER(MgpNoise), C.c_void_p]),
+    "mgp_e_log_p_y": (C.c_int, [C.c_void_p, C.POINTER(MgpLayer), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                C.c_int32, C.c_void_p, C.c_void_p]),
     "mgp_reduce_buffer_len": (C.c_int64, [C.POINTER(MgpLayer), C.POINTER(MgpLayer)]),
     "mgp_elbo_local": (C.c_int, [C.c_void_p, C.POINTER(MgpElboCfg), C.POINTER(MgpLayer), C.POINTER(MgpLayer),
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(MgpNoise),
@@ -85,6 +98,12 @@ _PROTOTYPES = {
                                    C.c_void_p, C.POINTER(MgpLayerGrad), C.POINTER(MgpLayerGrad), C.c_void_p,
                                    C.c_void_p]),
     "mgp_debug_kuu_chol": (C.c_int, [C.c_void_p, C.POINTER(MgpLayer), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mgp_adam_step": (C.c_int, [C.c_void_p, C.POINTER(MgpAdamSlot), C.c_int32, C.c_double, C.c_double, C.c_double,
+                                C.c_double, C.c_double, C.c_int64]),
+    "mgp_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
+                                  C.c_void_p]),
+    "mgp_kmeans_iterate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmgp.so")
-SOURCES = ["api.cu", "precompute.cu", "gemm_small.cu", "stream_kernels.cu", "syrk.cu", "mc_pass.cu"]
+SOURCES = ["api.cu", "precompute.cu", "gemm_small.cu", "stream_kernels.cu", "syrk.cu", "mc_pass.cu", "train_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

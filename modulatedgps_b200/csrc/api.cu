@@ -488,6 +488,57 @@ int mgp_predict_samples(mgp_ctx* c, const mgp_layer* pred, const mgp_layer* assi
     return MGP_OK;
 }
 
+int mgp_w_sample(mgp_ctx* c, const mgp_layer* assign, const double* X, int64_t N, int32_t S, double temperature,
+                 const mgp_noise* noise, double* W) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    if (N < 0 || S < 1 || !noise || !(temperature > 0.0) || (N > 0 && (!X || !W)))
+        return fail(c, MGP_ERR_BAD_ARG, "w_sample: bad arguments");
+    if ((noise->z == nullptr) != (noise->u == nullptr)) return fail(c, MGP_ERR_BAD_ARG, "w_sample: z and u must be given together");
+    if (N == 0) return MGP_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->pre_valid = false;
+    TRY(check_layer(c, assign));
+    const int K = assign->K;
+    TRY(ensure(c, c->scratch_rb, (size_t)N * K * 8 * 2));
+    double* fm = (double*)c->scratch_rb.p;
+    double* fv = fm + N * K;
+    const Launch ln = launch_of(c);
+    TRY(setup_layer(c, c->slot[1], assign, false));
+    precompute_layer(c->slot[1].dev, false, (int*)c->status.p, ln);
+    TRY(run_predict_f(c, c->slot[1], X, N, fm, fv));
+    SampleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.S = S; a.K = K; a.lik = 0; a.temperature = temperature; a.n = N;
+    a.fmean_a = fm; a.fvar_a = fv;
+    a.z = noise->z; a.u = noise->u; a.seed = noise->seed; a.point_offset = noise->point_offset;
+    w_sample_kernel(a, W, ln);
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
+int mgp_e_log_p_y(mgp_ctx* c, const mgp_layer* pred, int32_t lik, const double* lik_var, const double* X, const double* Y,
+                  int64_t N, int32_t S, const double* W, double* out) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    if (N < 0 || S < 1 || (N > 0 && (!X || !Y || !W || !out))) return fail(c, MGP_ERR_BAD_ARG, "e_log_p_y: bad arguments");
+    if (lik != MGP_LIK_GAUSSIAN && lik != MGP_LIK_MULTICLASS) return fail(c, MGP_ERR_BAD_ARG, "e_log_p_y: lik");
+    if (lik == MGP_LIK_GAUSSIAN && !lik_var) return fail(c, MGP_ERR_BAD_ARG, "e_log_p_y: Gaussian likelihood needs lik_var");
+    if (N == 0) return MGP_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    c->pre_valid = false;
+    TRY(check_layer(c, pred));
+    const int K = pred->K;
+    TRY(ensure(c, c->scratch_rb, (size_t)N * K * 8 * 2));
+    double* fm = (double*)c->scratch_rb.p;
+    double* fv = fm + N * K;
+    const Launch ln = launch_of(c);
+    TRY(setup_layer(c, c->slot[0], pred, false));
+    precompute_layer(c->slot[0].dev, false, (int*)c->status.p, ln);
+    TRY(run_predict_f(c, c->slot[0], X, N, fm, fv));
+    e_log_p_y_kernel(fm, fv, Y, lik_var, lik, W, S, N, K, out, ln);
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
 int64_t mgp_reduce_buffer_len(const mgp_layer* pred, const mgp_layer* assign) {
     if (!pred || !assign) return 0;
     const int Mp_p = (pred->M + 31) / 32 * 32, Mp_a = (assign->M + 31) / 32 * 32;

@@ -119,5 +119,10 @@ struct SampleArgs {
     double *samples_y, *samples_f;  // [S, n]
 };
 void predict_samples_kernel(const SampleArgs& a, const Launch& ln);
+// W [S, n, K]: relaxed one-hot sample of the assign layer's logits (uses fmean_a, fvar_a, z, u / Philox of SampleArgs)
+void w_sample_kernel(const SampleArgs& a, double* W_out, const Launch& ln);
+// out [n] = logsumexp_S(sum_k W ve) - log S for the expert likelihood `lik` (0 Gaussian, 1 MultiClass RobustMax)
+void e_log_p_y_kernel(const double* fmean, const double* fvar, const double* Y, const double* lik_var, int lik,
+                      const double* W, int S, int64_t n, int K, double* out, const Launch& ln);
 
 }  // namespace mgp

@@ -499,4 +499,90 @@ void predict_samples_kernel(const SampleArgs& a, const Launch& ln) {
     ln.tick();
 }
 
+// ==================================================================================================
+// SMGP.W_dist(...).sample and SMGP.E_log_p_Y as stand-alone calls (models.py:55-67): the ELBO path fuses them into
+// mc_pass; these exist so that code written against the reference's intermediate methods keeps working.
+// ==================================================================================================
+// W [S, n, K] = relaxed one-hot sample at temperature T of logits mu_a + z sqrt(var_a + jitter)
+template <int K>
+__global__ void w_sample_k(SampleArgs a, double* W_out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)a.S * a.n) return;
+    const int s = (int)(idx / a.n);
+    const int64_t i = idx % a.n;
+    double mu_a[K], sd_a[K], z[K], u[K], W[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        mu_a[k] = a.fmean_a[(size_t)i * K + k];
+        sd_a[k] = sqrt(a.fvar_a[(size_t)i * K + k] + REPARAM_JITTER);
+        if (a.z != nullptr) {
+            z[k] = a.z[((size_t)s * a.n + i) * K + k];
+            u[k] = a.u[((size_t)s * a.n + i) * K + k];
+        } else {
+            philox_draw(a.seed, a.point_offset + i, s, k, 0, z[k], u[k]);
+        }
+    }
+    sample_weights<K>(mu_a, sd_a, z, u, a.temperature, W);
+#pragma unroll
+    for (int k = 0; k < K; ++k) W_out[idx * K + k] = W[k];
+}
+
+void w_sample_kernel(const SampleArgs& a, double* W_out, const Launch& ln) {
+    const int64_t total = (int64_t)a.S * a.n;
+    if (total <= 0) return;
+    const unsigned grid = (unsigned)((total + 127) / 128);
+#define WS(KK) case KK: w_sample_k<KK><<<grid, 128, 0, ln.stream>>>(a, W_out); break;
+    switch (a.K) { WS(1) WS(2) WS(3) WS(4) WS(5) WS(6) WS(7) default: w_sample_k<8><<<grid, 128, 0, ln.stream>>>(a, W_out); }
+#undef WS
+    ln.tick();
+}
+
+// out[n] = logsumexp_s( sum_k W[s,n,k] ve[n,k] ) - log S,  ve = the expert likelihood's variational expectation
+template <int K>
+__global__ void e_log_p_y_k(const double* fmean, const double* fvar, const double* Y, const double* lik_var, int lik,
+                            const double* W, int S, int64_t n, double* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double mu[K], v[K], ve[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) { mu[k] = fmean[(size_t)i * K + k]; v[k] = fvar[(size_t)i * K + k]; }
+    const double y = Y[i];
+    if (lik == 0) {   // GaussianModified._variational_expectations, likelihoods.py:39-41 (per component)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double s2 = lik_var[k], r = y - mu[k];
+            ve[k] = -HALF_LOG_2PI - 0.5 * log(s2) - 0.5 * (r * r + v[k]) / s2;
+        }
+    } else {          // gpflow MultiClass(RobustMax): one value per point, broadcast over the components
+        const double eps = robustmax_eps();
+        double d0[K], d1[K];
+        int c = (int)y;
+        c = c < 0 ? 0 : (c >= K ? K - 1 : c);
+        const double p = robustmax_prob<K, false>(c, mu, v, d0, d1);
+        const double val = p * log(1.0 - eps) + (1.0 - p) * log(eps / (K - 1.0));
+#pragma unroll
+        for (int k = 0; k < K; ++k) ve[k] = val;
+    }
+    double m = -DBL_MAX, acc = 0.0;
+    for (int s = 0; s < S; ++s) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) t += W[((size_t)s * n + i) * K + k] * ve[k];
+        if (t > m) { acc = acc * exp(m - t) + 1.0; m = t; }
+        else acc += exp(t - m);
+    }
+    out[i] = m + log(acc) - log((double)S);
+}
+
+void e_log_p_y_kernel(const double* fmean, const double* fvar, const double* Y, const double* lik_var, int lik,
+                      const double* W, int S, int64_t n, int K, double* out, const Launch& ln) {
+    if (n <= 0) return;
+    ensure_gh(ln.stream);
+    const unsigned grid = (unsigned)((n + 127) / 128);
+#define EL(KK) case KK: e_log_p_y_k<KK><<<grid, 128, 0, ln.stream>>>(fmean, fvar, Y, lik_var, lik, W, S, n, out); break;
+    switch (K) { EL(1) EL(2) EL(3) EL(4) EL(5) EL(6) EL(7) default: e_log_p_y_k<8><<<grid, 128, 0, ln.stream>>>(fmean, fvar, Y, lik_var, lik, W, S, n, out); }
+#undef EL
+    ln.tick();
+}
+
 }  // namespace mgp

@@ -181,6 +181,36 @@ class _ElboFunction(torch.autograd.Function):
         return (None, None, None, None, None, None) + tuple(None if g is None else gout * g for g in ctx.grads)
 
 
+class _RelaxedAssignments:
+    """What SMGP.W_dist returns: `.sample(n)` draws relaxed one-hot assignment weights [n, S*N, K] (models.py:60,73)."""
+
+    def __init__(self, model, view, X, S, noise):
+        self.model, self.view, self.X, self.S, self.noise = model, view, X, int(S), noise
+        self.temperature = model.temperature
+
+    def sample(self, n=1):
+        X, S, K = self.X, self.S, self.view.K
+        N = X.shape[0]
+        ctx = _lib.get_context(X.device)
+        out = torch.empty(int(n), S, N, K, dtype=F64, device=X.device)
+        for r in range(int(n)):
+            keep = []
+            if self.noise is not None and r == 0:
+                z, u = (to_device_f64(a, X.device) for a in self.noise)
+                for a in (z, u):
+                    if tuple(a.shape) != (S, N, K):
+                        raise ValueError(f"noise arrays must have shape {(S, N, K)}; got {tuple(a.shape)}")
+                keep = [z, u]
+                nz = _lib.MgpNoise(z.data_ptr(), u.data_ptr(), 0, 0)
+            else:
+                self.model._step += 1
+                nz = _lib.MgpNoise(None, None, (self.model.seed << 20) + self.model._step, 0)
+            ctx.check(ctx.lib.mgp_w_sample(ctx.handle, C.byref(self.view.struct), _lib.ptr(X), N, S, float(self.temperature),
+                                           C.byref(nz), _lib.ptr(out[r])))
+            del keep
+        return _wrap(out.reshape(int(n), S * N, K))
+
+
 class SGP(Module):
     """Scalable GP: X -> Xt = integrate(X) -> GP -> Y   (MixtureGPs/models.py:23-41)."""
 
@@ -262,6 +292,36 @@ class SMGP(SGP):
             def closure():
                 return self.training_loss(data)
         return closure
+
+    def W_dist(self, X, noise=None):
+        """models.py:55-61: the relaxed one-hot (Gumbel-softmax, T = 1e-2) distribution over assignments of the points
+        in X ([S, N, D] as `integrate` returns it, or [N, D] with S = num_samples).  Like the TFP object the reference
+        gets back, it is consumed through `.sample(n)` -> [n, S*N, K].  noise = (z, u), each [S, N, K], fixes the
+        draw of `.sample(1)`; otherwise the device Philox stream is used."""
+        view = _LayerView(self.assign_layer)
+        Xd, S = _points(X, view.D)
+        return _RelaxedAssignments(self, view, Xd, int(self.num_samples) if S is None else S, noise)
+
+    def E_log_p_Y(self, X, Y, W_SND):
+        """models.py:63-67: logsumexp_S(sum_k W ve) - log S per point -> [N].  W_SND [S, N, K]."""
+        return _wrap(self._e_log_p_y(self.pred_layer, self.likelihood, X, Y, W_SND))
+
+    def _e_log_p_y(self, layer, likelihood, X, Y, W_SND):
+        view = _LayerView(layer)
+        Xd, _ = _points(X, view.D)
+        W = to_device_f64(W_SND, Xd.device)
+        N = Xd.shape[0]
+        if W.dim() != 3 or W.shape[1] != N or W.shape[2] != view.K:
+            raise ValueError(f"W_SND must be [S, {N}, {view.K}]; got {tuple(W.shape)}")
+        Yd = to_device_f64(Y, Xd.device).reshape(-1)
+        if Yd.numel() != N:
+            raise ValueError(f"Y has {Yd.numel()} rows but X has {N}")
+        ctx = _lib.get_context(Xd.device)
+        out = torch.empty(N, dtype=F64, device=Xd.device)
+        lik_var = likelihood.component_variances(view.K)
+        ctx.check(ctx.lib.mgp_e_log_p_y(ctx.handle, C.byref(view.struct), likelihood.kind, _lib.ptr(lik_var), _lib.ptr(Xd),
+                                        _lib.ptr(Yd), N, int(W.shape[0]), _lib.ptr(W), _lib.ptr(out)))
+        return out
 
     def predict_assign(self, Xnew, S=1):
         """models.py:85-89 -> softmax assignment probabilities [N, K]."""
@@ -430,6 +490,13 @@ class SMGPModified(SMGP):
 
     def _assign_lik_variances(self, K):
         return self.assign_likelihood.component_variances(K)
+
+    def E_log_p_Y(self, X, Y, W_SND):
+        """models.py:112-123: logsumexp_S of the assign layer's outputs scored against Y under `assign_likelihood`
+        plus logsumexp_S of the experts' term, each sum_k W ve - log S."""
+        term_a = self._e_log_p_y(self.assign_layer, self.assign_likelihood, X, Y, W_SND)
+        term_y = self._e_log_p_y(self.pred_layer, self.likelihood, X, Y, W_SND)
+        return _wrap(term_a + term_y)
 
     def _add_extra_param_grads(self, add, grads):
         add(self.assign_likelihood.likelihood.variance, grads["assign_lik_var"])

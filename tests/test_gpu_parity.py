@@ -294,7 +294,7 @@ def test_not_positive_definite_is_reported(hg):
 
 
 def test_training_reduces_loss_and_native_code_is_used(hg):
-    """A few Adam steps through run_adam's machinery: the loss goes down and kernels were launched by libmgp."""
+    """A few fused-Adam steps (run_adam's machinery): the loss goes down and kernels were launched by libmgp."""
     import modulatedgps_b200 as mg
     from modulatedgps_b200 import _lib
     case, X, Y, _, _ = _synthetic_case(2048, 2, 36, 3, 8, seed=11)
@@ -304,11 +304,120 @@ def test_training_reduces_loss_and_native_code_is_used(hg):
     opt = mg.make_adam(model, 0.01)
     losses = []
     for it in range(30):
-        opt.zero_grad(set_to_none=True)
         model._step = 0                     # common random numbers: compare like with like
-        loss = model._training_loss((X, Y))
-        loss.backward()
-        opt.step()
-        losses.append(float(loss))
+        losses.append(float(opt.minimize((X, Y))))
     assert losses[-1] < losses[0] - 0.05, losses[::5]
     assert _lib.total_launches() - before > 30 * 20
+
+
+def test_fused_adam_matches_the_tf_update_rule(hg):
+    """mgp_adam_step against TF 2.10 Keras Adam written out in torch on the UNCONSTRAINED gradients
+    that loss.backward() delivers: same variables after several steps, every bijector (identity, softplus,
+    fill-triangular) on the path.  utils/training_utils.py:6-10."""
+    import copy
+    import modulatedgps_b200 as mg
+    case, X, Y, z, u = _synthetic_case(300, 2, 36, 3, 4, seed=5)
+    lr, b1, b2, eps = 0.01, 0.9, 0.999, 1e-7
+    ma, mb = hg.build_model(copy.deepcopy(case)), hg.build_model(copy.deepcopy(case))
+    opt = mg.FusedAdam(ma, lr)
+    vars_b = list(mb.trainable_variables)
+    m = [torch.zeros_like(v) for v in vars_b]
+    v2 = [torch.zeros_like(v) for v in vars_b]
+    for step in range(1, 6):
+        opt.minimize((X, Y), noise=(z, u))
+        for w in vars_b:
+            w.grad = None
+        mb._training_loss((X, Y), noise=(z, u)).backward()
+        lr_t = lr * np.sqrt(1 - b2 ** step) / (1 - b1 ** step)
+        with torch.no_grad():
+            for w, mm, vv in zip(vars_b, m, v2):
+                g = w.grad
+                mm += (g - mm) * (1 - b1)
+                vv += (g * g - vv) * (1 - b2)
+                w -= lr_t * mm / (vv.sqrt() + eps)
+    for wa, wb in zip(ma.trainable_variables, vars_b):
+        assert relerr(wa.detach().cpu().numpy(), wb.detach().cpu().numpy()) <= 1e-10
+
+
+def test_device_minibatches_cover_an_epoch_exactly_once(hg):
+    """DeviceMinibatches: shuffle(N).batch(B).repeat() — every row once per epoch, rows intact,
+    short last batch, a new order in the next epoch."""
+    import modulatedgps_b200 as mg
+    rng = np.random.default_rng(0)
+    N, D, B = 1037, 3, 200
+    X = rng.standard_normal((N, D))
+    Y = X[:, :1] * 2.0 + 1.0                                  # exact in floating point: rows can be matched bit for bit
+    it = mg.DeviceMinibatches(X, Y, B, seed=1)
+    epochs = []
+    for _ in range(2):
+        rows, sizes = [], []
+        for _ in range((N + B - 1) // B):
+            xb, yb = next(it)
+            assert torch.equal(yb[:, 0], xb[:, 0] * 2.0 + 1.0)   # rows travel together
+            rows.append(xb.cpu().numpy())
+            sizes.append(xb.shape[0])
+        assert sizes == [B] * (N // B) + [N % B]
+        allrows = np.concatenate(rows)
+        assert np.array_equal(np.sort(allrows, axis=0), np.sort(X, axis=0))
+        epochs.append(allrows)
+    assert not np.array_equal(epochs[0], epochs[1])
+
+
+def test_kmeans_finds_the_clusters_scipy_finds(hg):
+    """kmeans (demos/demo_tf2.py:39): distortion no worse than scipy's on well-separated blobs."""
+    import modulatedgps_b200 as mg
+    from scipy.cluster.vq import kmeans as sk
+    rng = np.random.default_rng(3)
+    centers = np.array([[0.0, 0.0], [6.0, 1.0], [-3.0, 7.0], [8.0, 8.0], [2.0, -6.0]])
+    X = np.concatenate([c + 0.5 * rng.standard_normal((400, 2)) for c in centers])
+    code, dist = mg.kmeans(X, 5, iter=10, seed=0)
+    ref_code, ref_dist = sk(X, 5, iter=10, seed=0)
+    assert code.shape == (5, 2)
+    assert dist <= ref_dist * 1.02
+    # every true centre has a code nearby
+    d = np.linalg.norm(centers[:, None, :] - code[None, :, :], axis=2).min(1)
+    assert d.max() < 0.2
+    # 1-D observations and a user guess, as scipy accepts
+    code1, _ = mg.kmeans(X[:, 0], np.array([[0.0], [6.0]]))
+    assert code1.shape == (2, 1)
+
+
+def test_predict_samples_batched_equals_one_call(hg):
+    """The demos' chunked predict_samples loop (demo_tf2.py:62-68) stitches to the same shapes as one call."""
+    import modulatedgps_b200 as mg
+    case, X, Y, _, _ = _synthetic_case(700, 2, 36, 3, 4, seed=2)
+    model = hg.build_model(case)
+    ys, fs = mg.predict_samples_batched(model, X, S=6, batch=256)
+    assert tuple(ys.shape) == (6, 700, 1) and tuple(fs.shape) == (6, 700, 1)
+    assert torch.isfinite(ys).all() and torch.isfinite(fs).all()
+
+
+@pytest.mark.parametrize("model_kind,lik", [("SMGP", "gaussian"), ("SMGPModified", "gaussian"), ("SMGPModified", "multiclass")])
+def test_w_dist_and_e_log_p_y_match_the_oracle(model_kind, lik, hg):
+    """The reference's intermediate methods as stand-alone calls: W_dist(X).sample(1) (models.py:55-61,73-74) and
+    E_log_p_Y(X, Y, W) (models.py:63-67 / 112-123), against the oracle on explicit noise; their mean over the points
+    minus KL / num_data is the ELBO the fused path returns."""
+    from oracle import svgp_mixture as O
+    N, D, M, K, S = 400, 2, 36, 3, 6
+    case, X, Y, z, u = _synthetic_case(N, D, M, K, S, seed=9, model=model_kind)
+    if lik == "multiclass":
+        case["lik"] = "multiclass"
+        Y = np.random.default_rng(1).integers(0, K, (N, 1)).astype(np.float64)
+    model = hg.build_model(case)
+    Xt, _ = model.integrate(X, S)
+    W = model.W_dist(Xt, noise=(z, u)).sample(1)[0].reshape(S, N, K)
+    pred, assign = O.layer_from_numpy(case["pred"]), O.layer_from_numpy(case["assign"])
+    mu_a, var_a = O.conditional(O.as_t(X), assign)
+    Wref = O.relaxed_onehot_weights(mu_a, var_a, O.as_t(z), O.as_t(u))
+    assert np.abs(W.cpu().numpy() - Wref.numpy()).max() <= 1e-9
+    per_point = model.E_log_p_Y(Xt, Y, W)
+    assert tuple(per_point.shape) == (N,)
+    elbo_parts = float(per_point.mean()) - float(model.pred_layer.prior_kl() + model.assign_layer.prior_kl()) / case["num_data"]
+    alv = None if case["assign_lik_var"] is None else O.as_t(case["assign_lik_var"])
+    ref = float(O.elbo(case["model"], case["lik"], pred, assign, O.as_t(case["lik_var"]), alv, X, Y, z, u, case["num_data"]))
+    assert abs(elbo_parts - ref) <= RTOL * abs(ref)
+    fused, _ = model.elbo_and_grads(X, Y, noise=(z, u))
+    assert abs(float(fused) - ref) <= RTOL * abs(ref)
+    # rows of W are probability vectors; a Philox draw has the same shape
+    assert np.abs(W.sum(-1).cpu().numpy() - 1.0).max() <= 1e-12
+    assert tuple(model.W_dist(X).sample(2).shape) == (2, S * N, K)

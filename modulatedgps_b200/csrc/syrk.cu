@@ -18,6 +18,8 @@
 // 64); they are dealt 18 + 18 to the two halves, and the host plan gives diagonal pairs proportionally longer point
 // ranges (fewer splits) so that every CTA finishes at the same time.  Each CTA accumulates into its own slot of
 // `part` (no atomics; deterministic); reduce_partials sums the slots.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -33,6 +35,18 @@ constexpr int SY_NSTAGE = 4;
 constexpr int SY_AHEAD = 2;         // stages in flight beyond the current one (leaves one stage of slack for warp skew)
 template <int KC>
 __host__ __device__ constexpr int sy_stage() { return 2 * 64 * (KC + 4) + 2 * KC * KP; }  // doubles: AI, AJ, vbar[KC][K], mubar[KC][K]
+
+// A mubar needs every 64-row block of A exactly once.  It rides on OFF-diagonal pairs (the diagonal ones already are
+// the slowest CTAs of the integer split): block b < nb - 1 is the J operand of pair (b + 1, b); block nb - 1 is the I
+// operand of pair (nb - 1, 0); a single-block matrix uses its only pair.  0: none, 1: rows of I, 2: rows of J.
+__host__ __device__ inline int syrk_mraw_role(int I, int J, int kbase, int nb) {
+    if (kbase != 0) return 0;
+    if (nb == 1) return 1;
+    if (nb == 2) return (I == 1 && J == 0) ? 3 : 0;   // both blocks ride on the only off-diagonal pair
+    if (I == J + 1) return 2;
+    if (I == nb - 1 && J == 0) return 1;
+    return 0;
+}
 
 // fragment (mi, ni) of the 64x64 tile (8x8 fragments) owned by a warp of the given mode
 //   0 / 1 : off-diagonal pair, rows 0-31 / 32-63, all columns
@@ -98,7 +112,7 @@ struct SyrkSrc {
 // two bulk copies of A plus the vbar / mubar slabs.  One lane issues.
 template <int KC>
 __device__ __forceinline__ void syrk_produce(const SyrkWork& w, const SyrkSrc& src, double* ring, uint64_t* full,
-                                             uint64_t* empty, int s, int K, bool do_mraw) {
+                                             uint64_t* empty, int s, int K, int mrole) {
     constexpr int SY_STR = KC + 4;
     const int st = s % SY_NSTAGE;
     double* dst = ring + (size_t)st * sy_stage<KC>();
@@ -111,13 +125,13 @@ __device__ __forceinline__ void syrk_produce(const SyrkWork& w, const SyrkSrc& s
     if (src.rows_j > 0)
         bulk_g2s(dst + 64 * SY_STR, At + (size_t)w.J * 64 * SY_STR, (unsigned)(src.rows_j * SY_STR * sizeof(double)), &full[st]);
     bulk_g2s(dst + 2 * 64 * SY_STR, src.vbar + (size_t)tile * KC * K, slab, &full[st]);
-    if (do_mraw) bulk_g2s(dst + 2 * 64 * SY_STR + KC * KP, src.mubar + (size_t)tile * KC * K, slab, &full[st]);
+    if (mrole) bulk_g2s(dst + 2 * 64 * SY_STR + KC * KP, src.mubar + (size_t)tile * KC * K, slab, &full[st]);
 }
 
 template <int MODE, int KC>
 __device__ __forceinline__ void syrk_consumer(const SyrkWork& w, const SyrkSrc& src, double* ring, uint64_t* full,
                                               uint64_t* empty, int nstage, double* part, double* mraw_part, int Mp, int K,
-                                              bool do_mraw) {
+                                              int mrole) {
     constexpr int SY_STR = KC + 4, SY_STAGE = sy_stage<KC>();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int k = w.kbase + (warp >> 1);
@@ -127,34 +141,49 @@ __device__ __forceinline__ void syrk_consumer(const SyrkWork& w, const SyrkSrc& 
     for (int mi = 0; mi < 8; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 8; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-    double am[2] = {0.0, 0.0};
+    double am_i[2] = {0.0, 0.0}, am_j[2] = {0.0, 0.0};   // A mubar of this warp's 8 rows of block I / block J
 
     for (int s = 0; s < nstage; ++s) {
         const int st = s % SY_NSTAGE;
         const double* cur = ring + (size_t)st * SY_STAGE;
         if ((s % SY_CONSUMERS) == warp && s + SY_AHEAD < nstage && lane == 0)
-            syrk_produce<KC>(w, src, ring, full, empty, s + SY_AHEAD, K, do_mraw);
+            syrk_produce<KC>(w, src, ring, full, empty, s + SY_AHEAD, K, mrole);
         mbar_wait(&full[st], (unsigned)((s / SY_NSTAGE) & 1));
         if (live) {
             const double* AI = cur + g * SY_STR + t;
             const double* AJ = (MODE >= 2 ? cur : cur + 64 * SY_STR) + g * SY_STR + t;
             syrk_stage<MODE, KC>(AI, AJ, cur + 2 * 64 * SY_STR + t * K + k, K, acc);
         }
-        if (do_mraw) {   // warp w: rows I*64 + 8w .. +8 ; columns = components
-            const double* AIw = cur + (warp * 8 + g) * SY_STR + t;
+        if (mrole) {   // warp w: rows 8w .. 8w+8 of the 64-row block; columns = components
             const double* mb = cur + 2 * 64 * SY_STR + KC * KP + t * K + g;
+            if (mrole & 1) {
+                const double* Aw = cur + (warp * 8 + g) * SY_STR + t;
 #pragma unroll
-            for (int ks = 0; ks < KC / 4; ++ks) dmma(am, AIw[ks * 4], g < K ? mb[ks * 4 * K] : 0.0);
+                for (int ks = 0; ks < KC / 4; ++ks) dmma(am_i, Aw[ks * 4], g < K ? mb[ks * 4 * K] : 0.0);
+            }
+            if (mrole & 2) {
+                const double* Aw = cur + (64 + warp * 8 + g) * SY_STR + t;
+#pragma unroll
+                for (int ks = 0; ks < KC / 4; ++ks) dmma(am_j, Aw[ks * 4], g < K ? mb[ks * 4 * K] : 0.0);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
     }
-    if (do_mraw) {
+    if (mrole & 1) {
         const int row = w.I * 64 + warp * 8 + g;
         if (row < Mp) {
             double* p = mraw_part + ((size_t)w.slot * Mp + row) * KP + 2 * t;
-            p[0] += am[0];
-            p[1] += am[1];
+            p[0] += am_i[0];
+            p[1] += am_i[1];
+        }
+    }
+    if (mrole & 2) {
+        const int row = w.J * 64 + warp * 8 + g;
+        if (row < Mp) {
+            double* p = mraw_part + ((size_t)w.slot * Mp + row) * KP + 2 * t;
+            p[0] += am_j[0];
+            p[1] += am_j[1];
         }
     }
     if (live) {
@@ -186,8 +215,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) syrk_kernel(const SyrkWork* pla
     const int nstage = (int)((w.pend - w.pbeg) / KC);
     if (nstage <= 0) return;
     const bool diag = (w.I == w.J);
-    // the J == 0 tile column of component group 0 sees every row block of A exactly once: it also forms A mubar
-    const bool do_mraw = (w.J == 0 && w.kbase == 0);
+    const int mrole = syrk_mraw_role(w.I, w.J, w.kbase, (Mp + 63) / 64);
     const int rows_i = min(64, Mp - w.I * 64), rows_j = diag ? 0 : min(64, Mp - w.J * 64);
 
     if (rows_i < 64 || (!diag && rows_j < 64)) {   // rows past Mp are never copied: they must read as zero
@@ -204,17 +232,17 @@ __global__ void __launch_bounds__(SY_THREADS, 1) syrk_kernel(const SyrkWork* pla
 
     SyrkSrc src;
     src.A = A; src.vbar = vbar; src.mubar = mubar; src.Mp = Mp; src.rows_i = rows_i; src.rows_j = rows_j;
-    src.bytes = (unsigned)((rows_i + rows_j) * SY_STR * sizeof(double)) + (unsigned)(KC * K * sizeof(double)) * (do_mraw ? 2u : 1u);
+    src.bytes = (unsigned)((rows_i + rows_j) * SY_STR * sizeof(double)) + (unsigned)(KC * K * sizeof(double)) * (mrole ? 2u : 1u);
     if (warp == 0 && lane == 0)   // prologue: the first SY_AHEAD stages
-        for (int s = 0; s < SY_AHEAD && s < nstage; ++s) syrk_produce<KC>(w, src, smem, full, empty, s, K, do_mraw);
+        for (int s = 0; s < SY_AHEAD && s < nstage; ++s) syrk_produce<KC>(w, src, smem, full, empty, s, K, mrole);
     // ---- consumers ----
     const int half = warp & 1;
     if (!diag) {
-        if (half == 0) syrk_consumer<0, KC>(w, src, smem, full, empty, nstage, part, mraw_part, Mp, K, do_mraw);
-        else syrk_consumer<1, KC>(w, src, smem, full, empty, nstage, part, mraw_part, Mp, K, do_mraw);
+        if (half == 0) syrk_consumer<0, KC>(w, src, smem, full, empty, nstage, part, mraw_part, Mp, K, mrole);
+        else syrk_consumer<1, KC>(w, src, smem, full, empty, nstage, part, mraw_part, Mp, K, mrole);
     } else {
-        if (half == 0) syrk_consumer<2, KC>(w, src, smem, full, empty, nstage, part, mraw_part, Mp, K, do_mraw);
-        else syrk_consumer<3, KC>(w, src, smem, full, empty, nstage, part, mraw_part, Mp, K, do_mraw);
+        if (half == 0) syrk_consumer<2, KC>(w, src, smem, full, empty, nstage, part, mraw_part, Mp, K, mrole);
+        else syrk_consumer<3, KC>(w, src, smem, full, empty, nstage, part, mraw_part, Mp, K, mrole);
     }
 }
 
@@ -222,6 +250,12 @@ __global__ void __launch_bounds__(SY_THREADS, 1) syrk_kernel(const SyrkWork* pla
 // Units = (tile pair, component group) with weight 32 (off-diagonal) or 18 (diagonal) DMMA per k4-step and warp.
 // When there are fewer units than SMs, each unit's point range is split so that the CTA count is ~num_sms and the
 // per-CTA work (weight x points) is as even as the integer split counts allow.
+// relative cost of a diagonal-pair CTA per point (18 of 32 fragments per warp, but more operand loads per DMMA)
+static double syrk_diag_weight() {
+    static const double w = getenv("MGP_SYRK_DIAG_WT") ? atof(getenv("MGP_SYRK_DIAG_WT")) : 18.0;   // tuning hook
+    return w;
+}
+
 static void syrk_split_counts(int Mp, int K, int num_sms, std::vector<int>& I_of, std::vector<int>& J_of,
                               std::vector<int>& kb_of, std::vector<int>& ns_of) {
     const int nb = (Mp + 63) / 64, kgroups = (K + 3) / 4;
@@ -230,7 +264,8 @@ static void syrk_split_counts(int Mp, int K, int num_sms, std::vector<int>& I_of
         for (int J = 0; J <= I; ++J)
             for (int kg = 0; kg < kgroups; ++kg) {
                 I_of.push_back(I); J_of.push_back(J); kb_of.push_back(kg * 4);
-                wt.push_back((I == J ? 18.0 : 32.0) + ((J == 0 && kg == 0) ? 1.0 : 0.0));
+                const int role = syrk_mraw_role(I, J, kg * 4, nb);
+                wt.push_back((I == J ? syrk_diag_weight() : 32.0) + (double)((role & 1) + (role >> 1)));
             }
     const int nu = (int)wt.size();
     ns_of.assign(nu, 1);
@@ -278,8 +313,9 @@ int syrk_make_plan(int Mp, int K, int64_t n, int kc, int num_sms, std::vector<Sy
             w.I = I_of[u]; w.J = J_of[u]; w.kbase = kb_of[u]; w.slot = j;
             w.pbeg = nchunks * j / ns * SY_KC;
             w.pend = nchunks * (j + 1) / ns * SY_KC;
-            // (the J == 0 column of component group 0 also forms A mubar: one more DMMA per k4-step and warp)
-            const double wt = (I_of[u] == J_of[u] ? 18.0 : 32.0) + ((J_of[u] == 0 && kb_of[u] == 0) ? 1.0 : 0.0);
+            // (+1 DMMA per k4-step and warp for every row block whose A mubar rides on this pair)
+            const int role = syrk_mraw_role(I_of[u], J_of[u], kb_of[u], (Mp + 63) / 64);
+            const double wt = (I_of[u] == J_of[u] ? syrk_diag_weight() : 32.0) + (double)((role & 1) + (role >> 1));
             if (w.pend > w.pbeg) all.push_back({wt * (double)(w.pend - w.pbeg), w});
         }
     }

@@ -244,12 +244,14 @@ def main():
         torch.cuda.synchronize()
 
     # ---- resident-input timing -------------------------------------------------------------------
-    for _ in range(max(3, args.warmup)):
-        step(Xd, Yd)
-    barrier()
+    # the clock sampler (an nvidia-smi -lms subprocess) is started BEFORE the warm-up so that its start-up (NVML
+    # initialisation can stall the GPU for milliseconds) stays out of the timed region; samples under load are kept
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step(Xd, Yd)
+    barrier()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -536,10 +536,11 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_bwd_b_kernel(LayerDev ly, Ch
     constexpr int NF = NT / 8, STR = NT + 4;
     extern __shared__ __align__(16) double smem[];
     const int Mp = ly.Mp, Dp = ly.Dp, D = ly.D, XSTR = xs_stride(Dp), E = 1 + 2 * Dp;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // Abar tile landed (bulk copy) AND X rows staged: 2 arrivals
+    uint64_t* tfree = full + 1;                            // every warp has finished multiplying from T: 8 arrivals
     double* T = smem + SK_BAR_DOUBLES;
-    double* Xs = T + (size_t)Mp * STR;
-    double* xs2 = Xs + NT * XSTR;
+    double* Xsb = T + (size_t)Mp * STR;                    // [2]{[NT][XSTR], [NT]} scaled X rows, by tile parity
+    const int xs_elems = NT * XSTR + NT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nb16 = Mp / 16, C4 = Mp / 4;
     const size_t tile_elems = (size_t)Mp * STR;
@@ -550,25 +551,38 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_bwd_b_kernel(LayerDev ly, Ch
     auto seg_of = [&](int i) { const int b = snake_block(i, warp, nb16); return Seg{ly.W_LinvT, 2 * b, 4 * b}; };
     WFrag wf;
     if (nmy > 0) wfrag_load(wf, seg_of(0), C4, seg_of(0).kb0, lane);
-    if (threadIdx.x == 0) { mbar_init(full, 1); mbar_fence_init(); }
+    if (threadIdx.x == 0) { mbar_init(full, 2); mbar_init(tfree, SK_WARPS); mbar_fence_init(); }
     __syncthreads();
+    // The per-fragment epilogue does not read T, so the NEXT tile's bulk copy is issued as soon as every warp has left
+    // the multiply phase (tfree) and flies while the epilogues run; X rows are staged into the other Xs buffer by
+    // warp 1 at the same point.  No CTA-wide barrier in the loop.
+    auto load_tile = [&](int tile) {   // thread 0
+        mbar_arrive_expect_tx(full, tile_bytes);
+        bulk_g2s(T, cb.A + (size_t)tile * tile_elems, tile_bytes, full);
+    };
+    auto stage_x = [&](int tile, int it) {   // warp 1
+        double* Xs = Xsb + (size_t)(it & 1) * xs_elems;
+        stage_x_warp<NT>(ly, cb, (int64_t)tile * NT, Xs, Xs + NT * XSTR, lane);
+        if (lane == 0) mbar_arrive(full);
+    };
+    if ((int)blockIdx.x < ntiles) {
+        if (threadIdx.x == 0) load_tile(blockIdx.x);
+        if (warp == 1) stage_x(blockIdx.x, 0);
+    }
 
-    unsigned phase = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t n0 = (int64_t)tile * NT;
-        if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(full, tile_bytes);
-            bulk_g2s(T, cb.A + (size_t)tile * tile_elems, tile_bytes, full);
-        }
-        if (warp == 1) stage_x_warp<NT>(ly, cb, n0, Xs, xs2, lane);
-        __syncthreads();
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const double* Xs = Xsb + (size_t)(it & 1) * xs_elems;
+        const double* xs2 = Xs + NT * XSTR;
+        const unsigned phase = (unsigned)(it & 1);
         mbar_wait(full, phase);
-        phase ^= 1u;
+        if (nmy == 0) { __syncwarp(); if (lane == 0) mbar_arrive(tfree); }
         for (int i = 0; i < nmy; ++i) {
             const int b = snake_block(i, warp, nb16);
             double acc[2][NF][2];
             zero_acc<NF>(acc);
             wgemm_seg<NT>(seg_of(i), C4, C4, T, acc, lane, wf, seg_of(i + 1 < nmy ? i + 1 : 0));   // upper triangular
+            if (i == nmy - 1) { __syncwarp(); if (lane == 0) mbar_arrive(tfree); }   // this warp is done with T
 #pragma unroll
             for (int mf = 0; mf < 2; ++mf) {
                 double kv[NF][2];
@@ -606,7 +620,14 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_bwd_b_kernel(LayerDev ly, Ch
                 }
             }
         }
-        __syncthreads();   // everyone is done with T and Xs before the next tile overwrites them
+        const int next = tile + gridDim.x;
+        if (warp <= 1 && next < ntiles) {
+            // tfree(it) also tells that every warp has finished the epilogue of tile it - 1 (it comes before its
+            // arrival in program order), i.e. nobody still reads the Xs buffer about to be refilled
+            mbar_wait(tfree, phase);
+            if (threadIdx.x == 0) load_tile(next);
+            if (warp == 1) stage_x(next, it + 1);
+        }
     }
 }
 
@@ -714,7 +735,7 @@ void cond_bwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
 void cond_bwd_b(const LayerDev& ly, const ChunkBuffers& cb, double* esum_part, int nparts_cap, int* nparts,
                 const Launch& ln) {
     const int NT = cb.tw;
-    const size_t smem = ((size_t)SK_BAR_DOUBLES + (size_t)ly.Mp * (NT + 4) + NT * xs_stride(ly.Dp) + NT) * sizeof(double);
+    const size_t smem = ((size_t)SK_BAR_DOUBLES + (size_t)ly.Mp * (NT + 4) + 2 * (NT * xs_stride(ly.Dp) + NT)) * sizeof(double);
     const int ntiles = (int)((cb.n + NT - 1) / NT);
     auto launch = [&](auto kernel) {
         const int grid = occupancy_grid(kernel, SK_CTHREADS, smem, ntiles, nparts_cap, ln);

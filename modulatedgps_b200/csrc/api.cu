@@ -3,8 +3,10 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -88,6 +90,9 @@ struct mgp_ctx {
     LayerSlot slot[2];
     Buf mc_part, scratch_rb, kl, status;
     bool pre_valid = false;
+    bool pick_valid = false;
+    int64_t pick_key[5] = {0, 0, 0, 0, 0};
+    int64_t pick_value = 0;
     std::vector<void*> owned;
 };
 
@@ -245,6 +250,19 @@ void join_side(mgp_ctx* c) {
     cudaStreamWaitEvent(c->stream, c->ev_join, 0);
 }
 
+// host-side stall finder (MGP_HOST_PROFILE=1): prints any bracketed host section that takes longer than 2 ms
+struct HostTimer {
+    const char* what;
+    std::chrono::steady_clock::time_point t0;
+    static bool on() { static const bool v = getenv("MGP_HOST_PROFILE") != nullptr; return v; }
+    explicit HostTimer(const char* w) : what(w) { if (on()) t0 = std::chrono::steady_clock::now(); }
+    ~HostTimer() {
+        if (!on()) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 2.0) fprintf(stderr, "[mgp host] %s took %.2f ms\n", what, ms);
+    }
+};
+
 struct Timed {   // RAII stage bracket
     mgp_ctx* c;
     Timed(mgp_ctx* ctx, int stage) : c(ctx) { c->timer.begin(stage, c->stream); }
@@ -252,7 +270,20 @@ struct Timed {   // RAII stage bracket
 };
 
 // points per chunk so that the materialised A of `nlayers` layers fits the budget
+int64_t pick_chunk_uncached(mgp_ctx* c, int64_t N, int Mp_max, int nlayers, int kcopies);
 int64_t pick_chunk(mgp_ctx* c, int64_t N, int Mp_max, int nlayers, int kcopies) {
+    // cudaMemGetInfo stalls the host for 3-80 ms every few calls (measured on the B200 box): ask once per distinct
+    // request, not once per step
+    const int64_t key[5] = {N, Mp_max, nlayers, kcopies, c->chunk_cap};
+    if (c->pick_valid && memcmp(key, c->pick_key, sizeof(key)) == 0) return c->pick_value;
+    const int64_t v = pick_chunk_uncached(c, N, Mp_max, nlayers, kcopies);
+    memcpy(c->pick_key, key, sizeof(key));
+    c->pick_value = v;
+    c->pick_valid = true;
+    return v;
+}
+
+int64_t pick_chunk_uncached(mgp_ctx* c, int64_t N, int Mp_max, int nlayers, int kcopies) {
     int64_t cap = c->chunk_cap;
     if (cap <= 0) {
         size_t free_b = 0, total_b = 0;
@@ -567,6 +598,7 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
     CUDA_TRY(c, cudaMemsetAsync(reduce_buf, 0, sizeof(double) * ra.end, c->stream));
 
     {
+        HostTimer ht("precompute launches");
         Timed t(c, ST_PRECOMPUTE);
         const Launch ls = fork_side(c);
         precompute_layer(sp.dev, true, (int*)c->status.p, ln);
@@ -577,8 +609,10 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
     if (N_local == 0) return MGP_OK;   // an empty shard contributes zeros
 
     const int Mp_max = sp.dev.Mp > sa.dev.Mp ? sp.dev.Mp : sa.dev.Mp;
-    const int64_t Nc = pick_chunk(c, N_local, Mp_max, 2, K);
+    int64_t Nc;
+    { HostTimer ht("pick_chunk (cudaMemGetInfo)"); Nc = pick_chunk(c, N_local, Mp_max, 2, K); }
     const int64_t ldn = round_up64(Nc, 64);
+    HostTimer ht_rest("elbo_local after pick_chunk");
     TRY(ensure_chunk(c, sp, ldn, true));
     TRY(ensure_chunk(c, sa, ldn, true));
     const int maxparts = stream_max_parts(ln);
@@ -603,10 +637,10 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
         ChunkBuffers cp = chunk_of(sp, X + c0 * D, n, ldn), ca = chunk_of(sa, X + c0 * D, n, ldn);
         cp.Bk = (double*)sp.Bk.p;
         ca.Bk = (double*)sa.Bk.p;
-        { Timed t(c, ST_COND_FWD_A); cond_fwd_a(sp.dev, cp, ln); }
-        { Timed t(c, ST_COND_FWD_B); cond_fwd_b(sp.dev, cp, ln); }
-        { Timed t(c, ST_COND_FWD_A); cond_fwd_a(sa.dev, ca, ln); }
-        { Timed t(c, ST_COND_FWD_B); cond_fwd_b(sa.dev, ca, ln); }
+        { HostTimer ht("fwd_a p"); Timed t(c, ST_COND_FWD_A); cond_fwd_a(sp.dev, cp, ln); }
+        { HostTimer ht("fwd_b p"); Timed t(c, ST_COND_FWD_B); cond_fwd_b(sp.dev, cp, ln); }
+        { HostTimer ht("fwd_a a"); Timed t(c, ST_COND_FWD_A); cond_fwd_a(sa.dev, ca, ln); }
+        { HostTimer ht("fwd_b a"); Timed t(c, ST_COND_FWD_B); cond_fwd_b(sa.dev, ca, ln); }
         McArgs m;
         m.model = cfg->model; m.lik = cfg->lik; m.S = cfg->S; m.K = K;
         m.temperature = cfg->temperature;
@@ -618,12 +652,13 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
         m.lik_var = lik_var; m.assign_lik_var = assign_lik_var;
         m.z = noise->z; m.u = noise->u; m.seed = noise->seed; m.point_offset = noise->point_offset;
         {
+            HostTimer ht("mc_pass");
             Timed t(c, ST_MC_PASS);
             mc_pass(m, (double*)c->mc_part.p, ln);
             mc_fold((double*)c->mc_part.p, mc_num_blocks(ldc), reduce_buf, ln);
         }
-        TRY(ensure_syrk_plan(c, sp, n));
-        TRY(ensure_syrk_plan(c, sa, n));
+        { HostTimer ht("syrk plan"); TRY(ensure_syrk_plan(c, sp, n)); TRY(ensure_syrk_plan(c, sa, n)); }
+        HostTimer ht_bwd("syrk + bwd launches");
         { Timed t(c, ST_SYRK); syrk_accumulate(sp.dev, cp, (const SyrkWork*)sp.syrk_plan.p, sp.plan_len, (double*)sp.syrk_part.p, (double*)sp.mraw_part.p, ln); }
         { Timed t(c, ST_SYRK); syrk_accumulate(sa.dev, ca, (const SyrkWork*)sa.syrk_plan.p, sa.plan_len, (double*)sa.syrk_part.p, (double*)sa.mraw_part.p, ln); }
         { Timed t(c, ST_COND_BWD_A); cond_bwd_a(sp.dev, cp, ln); }

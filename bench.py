@@ -193,9 +193,11 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
-    # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; rank 0's stdout must stay ONE JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # NCCL prints its version banner on STDOUT (C stdio) when the communicator is created; rank 0's stdout must stay
+    # ONE JSON line, so file descriptor 1 points at stderr until the line is printed
+    sys.stdout.flush()
+    saved_stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -285,12 +287,20 @@ def main():
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_host0 = time.perf_counter()
     e2.record()
+    trace = []
     for _ in range(args.steps):
+        ta = time.perf_counter()
         xd = Xh.to(dev, non_blocking=True)
         yd = Yh.to(dev, non_blocking=True)
+        tb = time.perf_counter()
         loss = step(xd, yd)
+        tc = time.perf_counter()
         _ = loss.item()
+        trace.append((1e3 * (tb - ta), 1e3 * (tc - tb), 1e3 * (time.perf_counter() - tc)))
     e3.record()
+    if os.environ.get("BENCH_TRACE") and rank == 0:
+        for r in trace:
+            print("e2e step: h2d-issue %.2f ms, launch %.2f ms, wait %.2f ms" % r, file=sys.stderr)
     barrier()
     t_host = time.perf_counter() - t_host0
     ms2 = torch.tensor([max(e2.elapsed_time(e3), 0.0)], dtype=torch.float64, device=dev)
@@ -352,7 +362,10 @@ def main():
                                     "note": "CPU restatement of the TF2/GPflow path; TF/GPflow are not installable here"}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout_fd, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)                        # NCCL also warns on stdout while the communicator is torn down
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -132,12 +132,15 @@ __device__ __forceinline__ void sample_weights(const double (&mu_a)[K], const do
         x[k] = (gumbel + logit) / temperature;
         mx = fmax(mx, x[k]);
     }
+    // exp(log_softmax(x))_k = exp(x_k - mx) / sum_j exp(x_j - mx): the K exponentials are formed once and normalised
+    // (TFP evaluates exp(x - mx - log(sum)); the two differ by a few ulp, far inside the 1e-9 parity bar)
+    double ex[K];
     double se = 0.0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) se += exp(x[k] - mx);
-    const double lse = log(se);
+    for (int k = 0; k < K; ++k) { ex[k] = exp(x[k] - mx); se += ex[k]; }
+    const double inv = 1.0 / se;
 #pragma unroll
-    for (int k = 0; k < K; ++k) W[k] = exp((x[k] - mx) - lse);
+    for (int k = 0; k < K; ++k) W[k] = ex[k] * inv;
 }
 
 // softmax-over-samples weighted accumulators of one logsumexp term, online (flash-attention style)

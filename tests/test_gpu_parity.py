@@ -140,7 +140,8 @@ def _synthetic_case(N, D, M, K, S, seed, model="SMGP", ls_assign=1.1):
                                        (210, 3, 480, 3, 4),     # NT 16, 2-deep ring, producer warp
                                        (130, 8, 640, 5, 3),     # NT 16, 2-deep ring, rotating producer duty
                                        (300, 8, 1024, 8, 4),    # BASELINE config #5's M, K: NT 16, single buffer
-                                       (90, 4, 1200, 2, 3)])    # largest accumulator variant
+                                       (90, 4, 1200, 2, 3),     # largest accumulator variant
+                                       (200, 20, 64, 2, 3)])    # wide inputs (D = 20: five k4-steps of the r^2 contraction)
 def test_oracle_sized_synthetic_vs_oracle(N, D, M, K, S, hg):
     """BASELINE config #4 / #5 shapes at an N the CPU oracle finishes in seconds; ragged N on purpose."""
     from oracle import svgp_mixture as O
@@ -149,10 +150,16 @@ def test_oracle_sized_synthetic_vs_oracle(N, D, M, K, S, hg):
     elbo, grads = model.elbo_and_grads(X, Y, noise=(z, u))
     ref, rg = O.elbo_and_grads(case["model"], case["lik"], O.layer_from_numpy(case["pred"]), O.layer_from_numpy(case["assign"]),
                                O.as_t(case["lik_var"]), None, X, Y, z, u, case["num_data"])
+    # 1e-9 wherever float64 allows it: a layer whose Kuu has cond > 1e5 gets the conditioning noise floor
+    # 100 * eps * cond(Kuu) instead (only the M >= 1024 random-Z cases come near it)
+    eps = np.finfo(np.float64).eps
+    tol = {name: max(RTOL, 100 * eps * float(np.linalg.cond(O.kuu(O.layer_from_numpy(case[name])).numpy())))
+           for name in ("pred", "assign")}
     assert abs(float(elbo) - ref) <= RTOL * abs(ref)
     for k, r in rg.items():
         mine = grads[k].cpu().numpy().reshape(r.shape)
-        assert relerr(mine, r) <= RTOL, (k, relerr(mine, r))
+        t = tol[k.split(".")[0]] if "." in k else max(tol.values())
+        assert relerr(mine, r) <= t, (k, relerr(mine, r), t)
 
 
 def test_ill_conditioned_kuu_stays_within_the_conditioning_noise_floor(hg):

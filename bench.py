@@ -314,8 +314,10 @@ def main():
         # dominant kernel and its algorithmic flops per step on this rank (per layer:
         # cond_fwd_a M^2, cond_fwd_b K M^2, syrk K M^2, cond_bwd_a K M^2, cond_bwd_b M^2 (+ the M^2 of the L-bar
         # reduction, which this design folds into the S_k algebra); x2 layers)
+        # (the survey's F_pt also counts an M^2 L-bar reduction per layer that the S_k formulation removes altogether:
+        #  it is part of step_roofline's flops_per_point, not of any kernel's algorithmic work)
         alg = {"cond_fwd_a": 2 * M * M, "cond_fwd_b": 2 * K * M * M, "syrk": 2 * K * M * M, "cond_bwd_a": 2 * K * M * M,
-               "cond_bwd_b": 2 * 2 * M * M}
+               "cond_bwd_b": 2 * M * M}
         # executed = algorithmic x the padding of the triangular blocking (16-row blocks: 17/16; SYRK: 528 computed
         # 8x8 fragments for 514 algorithmic ones)
         executed = {"cond_fwd_a": 2 * M * M * 17 / 16, "cond_fwd_b": 2 * K * M * M * 17 / 16, "syrk": 2 * K * M * M * 528 / 514,

@@ -200,6 +200,77 @@ __global__ void wloop_pf(const double* W, int Mp, int nmat, int iters, double* o
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// two 16-row blocks (e.g. the same rows of two components' matrices) multiplied against the SAME right operand at once:
+// 4 A fragments + 4 B fragments feed 16 DMMAs per k4-step (16 accumulator chains, half the LDS per DMMA)
+struct WFrag4 { double a[4][4]; };
+__device__ __forceinline__ void wfrag4_load(WFrag4& f, const double* wA, const double* wB, int rb8, int C4, int kb, int lane) {
+    const double* p0 = wA + ((size_t)rb8 * C4 + kb) * 32 + lane;
+    const double* p1 = wB + ((size_t)rb8 * C4 + kb) * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        f.a[0][j] = __ldg(p0 + j * 32); f.a[1][j] = __ldg(p0 + (size_t)C4 * 32 + j * 32);
+        f.a[2][j] = __ldg(p1 + j * 32); f.a[3][j] = __ldg(p1 + (size_t)C4 * 32 + j * 32);
+    }
+}
+template <int NT>
+__global__ void __launch_bounds__(256, 1) wloop_dual(const double* W, int Mp, int nmat, int iters, double* out) {
+    constexpr int NF = NT / 8, STR = NT + 4;
+    extern __shared__ double T[];
+    for (int i = threadIdx.x; i < Mp * STR; i += blockDim.x) T[i] = 1e-3 * (i % 13);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int nb16 = Mp / 16, C4 = Mp / 4;
+    const double* tb = T + t * STR + g;
+    double acc[4][NF][2];
+#pragma unroll
+    for (int mf = 0; mf < 4; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) acc[mf][nf][0] = acc[mf][nf][1] = 0.0;
+    WFrag4 f, n;
+    int b = warp % nb16, m = 0;
+    wfrag4_load(f, W, W + (size_t)Mp * Mp, 2 * b, C4, 0, lane);
+    for (int it = 0; it < iters; ++it) {
+        const double* wA = W + (size_t)m * Mp * Mp;
+        const double* wB = W + (size_t)((m + 1) % nmat) * Mp * Mp;
+        int nb = b + 8, nm = m;
+        if (nb >= nb16) { nb -= nb16; nm = (m + 2) % nmat; }
+        const double* nA = W + (size_t)nm * Mp * Mp;
+        const double* nB = W + (size_t)((nm + 1) % nmat) * Mp * Mp;
+        for (int kb = 0; kb < C4; kb += 8) {
+            wfrag4_load(n, wA, wB, 2 * b, C4, kb + 4, lane);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double* tr = tb + (size_t)(kb + j) * 4 * STR;
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) {
+                    const double bb = tr[nf * 8];
+#pragma unroll
+                    for (int mf = 0; mf < 4; ++mf) dmma(acc[mf][nf], f.a[mf][j], bb);
+                }
+            }
+            if (kb + 8 < C4) wfrag4_load(f, wA, wB, 2 * b, C4, kb + 8, lane);
+            else wfrag4_load(f, nA, nB, 2 * nb, C4, 0, lane);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double* tr = tb + (size_t)(kb + 4 + j) * 4 * STR;
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) {
+                    const double bb = tr[nf * 8];
+#pragma unroll
+                    for (int mf = 0; mf < 4; ++mf) dmma(acc[mf][nf], n.a[mf][j], bb);
+                }
+            }
+        }
+        b = nb; m = nm;
+    }
+    double s = 0;
+#pragma unroll
+    for (int mf = 0; mf < 4; ++mf)
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf) s += acc[mf][nf][0] + acc[mf][nf][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 int main() {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
     const int nsm = p.multiProcessorCount, Mp = 256, nmat = 4;
@@ -248,6 +319,8 @@ int main() {
     run(wloop_pf<32, 2>, 32, 1, 256);
     run(wloop_pf<32, 3>, 32, 1, 256);
     run(wloop_pf<32, 4>, 32, 1, 256);
+    printf("two 16-row blocks per warp against one right operand (16 chains, 8 warps); flops = 2x per iteration:\n");
+    run(wloop_dual<32>, 32, 1, 256, 1);
     fill(true);
     printf("same with random W (data-dependent power / clocks?):\n");
     run(wloop_pp<32, 1>, 32, 1, 256);

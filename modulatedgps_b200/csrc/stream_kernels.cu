@@ -125,6 +125,62 @@ __device__ __forceinline__ void wgemm_seg(const Seg& cur, int kb1, int C4, const
     }
 }
 
+// Copy-free variant (used by cond_fwd_b, where it gains 1.3 %; the two-CTA kernels and cond_bwd_a lose with the second
+// set live across their epilogues).  `a` and `b` are the two fragment register sets.  On entry `a` holds the first group of `cur`.  Returns true if, on
+// exit, the first group of `nxt` sits in `b` (odd number of groups: the sets have swapped roles) and false if it
+// sits in `a` — there is NO register copy: after a copy-based odd step every DMMA of the next group waited for the
+// loads the copy had to wait for.  Callers keep both sets alive and alternate the argument order (WPair::run).
+template <int NT>
+__device__ __forceinline__ bool wgemm_seg_sw(const Seg& cur, int kb1, int C4, const double* Tsm, double (&acc)[2][NT / 8][2],
+                                          int lane, WFrag& a, WFrag& b, const Seg& nxt) {
+    constexpr int STR = NT + 4;
+    const int g = lane >> 2, t = lane & 3;
+    const double* tb = Tsm + t * STR + g;
+    // fragment pointers of this lane: group at k4-block kb of `cur` is at wc + kb * 32 (second row block + C4 * 32)
+    const double* wc = cur.w + (size_t)cur.rb8 * C4 * 32 + lane;
+    const double* wn = nxt.w + ((size_t)nxt.rb8 * C4 + nxt.kb0) * 32 + lane;
+    const size_t rstride = (size_t)C4 * 32;
+    auto load = [&](WFrag& d, const double* w0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            d.a0[j] = __ldg(w0 + j * 32);
+            d.a1[j] = __ldg(w0 + rstride + j * 32);
+        }
+    };
+    int kb = cur.kb0;
+    const bool odd = ((kb1 - kb) >> 2) & 1;
+    if (!odd) {
+        for (; kb < kb1; kb += 8) {
+            load(b, wc + (size_t)(kb + 4) * 32);
+            wgemm_group<NT>(a, tb, kb, acc);
+            load(a, (kb + 8 < kb1) ? wc + (size_t)(kb + 8) * 32 : wn);
+            wgemm_group<NT>(b, tb, kb + 4, acc);
+        }
+        return false;
+    }
+    load(b, (kb + 4 < kb1) ? wc + (size_t)(kb + 4) * 32 : wn);
+    wgemm_group<NT>(a, tb, kb, acc);
+    kb += 4;
+    for (; kb < kb1; kb += 8) {   // roles swapped: b is current
+        load(a, wc + (size_t)(kb + 4) * 32);
+        wgemm_group<NT>(b, tb, kb, acc);
+        load(b, (kb + 8 < kb1) ? wc + (size_t)(kb + 8) * 32 : wn);
+        wgemm_group<NT>(a, tb, kb + 4, acc);
+    }
+    return true;
+}
+// the two fragment sets of a warp and which of them currently holds the next group
+struct WPair {
+    WFrag f, n;
+    bool sw = false;
+    template <int NT>
+    __device__ __forceinline__ void run(const Seg& cur, int kb1, int C4, const double* Tsm, double (&acc)[2][NT / 8][2],
+                                        int lane, const Seg& nxt) {
+        if (!sw) { if (wgemm_seg_sw<NT>(cur, kb1, C4, Tsm, acc, lane, f, n, nxt)) sw = true; }
+        else { if (wgemm_seg_sw<NT>(cur, kb1, C4, Tsm, acc, lane, n, f, nxt)) sw = false; }
+    }
+};
+
 // Xs[n][d] = X[n0+n][d] / lengthscale_d (0 outside the chunk / padding); xs2[n] = |Xs_n|^2.  One warp.
 template <int NT>
 __device__ __forceinline__ void stage_x_warp(const LayerDev& ly, const ChunkBuffers& cb, int64_t n0, double* Xs,
@@ -315,8 +371,8 @@ __global__ void __launch_bounds__(SK_CTHREADS + 32, 1) cond_fwd_b_kernel(LayerDe
         const int b = snake_block(r, warp, nb16);
         return Seg{ly.W_LqT + (size_t)k * Mp * Mp, 2 * b, 4 * b};
     };
-    WFrag wf;
-    if (nmy > 0) { const Seg s0 = seg_of(0, 0); wfrag_load(wf, s0, C4, s0.kb0, lane); }
+    WPair wp;
+    if (nmy > 0) { const Seg s0 = seg_of(0, 0); wfrag_load(wp.f, s0, C4, s0.kb0, lane); }
     for (int i = 0; i < my_tiles; ++i) {
         const int buf = i % NBUF;
         const int64_t tile = tile_of(i);
@@ -334,7 +390,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + 32, 1) cond_fwd_b_kernel(LayerDe
                 double acc[2][NF][2];
                 zero_acc<NF>(acc);
                 const Seg nxt = (r + 1 < nmy) ? seg_of(k, r + 1) : seg_of(k + 1 < K ? k + 1 : 0, 0);
-                wgemm_seg<NT>(seg_of(k, r), C4, C4, T, acc, lane, wf, nxt);   // upper triangular
+                wp.template run<NT>(seg_of(k, r), C4, C4, T, acc, lane, nxt);   // upper triangular
 #pragma unroll
                 for (int mf = 0; mf < 2; ++mf)
 #pragma unroll

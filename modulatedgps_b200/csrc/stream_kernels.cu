@@ -440,8 +440,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + 32, 1) cond_fwd_b_kernel(LayerDe
 // per point tile the ring carries K + 1 stages (B_0 .. B_{K-1}, then A for the elementwise epilogue); each warp keeps
 // the accumulators of ALL its row blocks (NBW of them) in registers across the stages of a tile.
 // PROD_WARP: warp 8 feeds the ring; otherwise (accumulators too large for the 168-register cap of a 9-warp CTA: three
-// warps on one SM sub-partition) the producer duty rotates over the consumer warps: at the start of stage j, warp
-// j % 8 waits for every warp to leave stage j - 1 and refills that buffer with stage j + NBUF - 1.
+// warps on one SM sub-partition) the last warp to leave a stage refills its buffer (shared-memory arrival counter).
 // ==================================================================================================
 template <int NT, int NBUF, int NBW, bool PROD_WARP>
 __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
@@ -451,6 +450,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
     const int Mp = ly.Mp, K = ly.K;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* done = full + NBUF;
+    unsigned* left = reinterpret_cast<unsigned*>(done + NBUF);   // !PROD_WARP: warps that have left the stage in buffer b
     double* Tb = smem + SK_BAR_DOUBLES;                // [NBUF][Mp][STR]
     double* mub = Tb + (size_t)NBUF * Mp * STR;        // [2][NT][K]  mubar slab of the tile (by tile parity)
     double* vbs = mub + 2 * NT * KP;                   // [2][NT][K]  vbar slab
@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
     const unsigned tile_bytes = (unsigned)(tile_elems * sizeof(double));
     const unsigned slab_bytes = (unsigned)(NT * K * sizeof(double));
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], SK_WARPS); }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], SK_WARPS); left[i] = 0u; }
         mbar_fence_init();
     }
     __syncthreads();
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
     auto issue = [&](int j) {
         const int ti = j / (K + 1), s = j - ti * (K + 1), buf = j % NBUF;
         const int64_t tile = tile_of(ti);
-        if (j >= NBUF) mbar_wait(&done[buf], (unsigned)(((j / NBUF) - 1) & 1));
+        if (PROD_WARP && j >= NBUF) mbar_wait(&done[buf], (unsigned)(((j / NBUF) - 1) & 1));
         mbar_arrive_expect_tx(&full[buf], tile_bytes + (s == 0 ? 2 * slab_bytes : 0u));
         const double* src = (s < K) ? cb.Bk + ((size_t)s * cb.tiles_cap + tile) * tile_elems : cb.A + (size_t)tile * tile_elems;
         bulk_g2s(Tb + (size_t)buf * tile_elems, src, tile_bytes, &full[buf]);
@@ -495,17 +495,25 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
     };
     WFrag wf;
     if (nmy > 0) wfrag_load(wf, seg_of(0, 0), C4, 0, lane);
+    // q_mu fragments of this warp's row blocks: the same for every tile, so they are read once (when the warp has
+    // few enough row blocks for them to stay in registers)
+    constexpr bool HOIST_WM = NBW <= 2;
+    double wm[HOIST_WM ? NBW : 1][2][KP / 4];
+#pragma unroll
+    for (int r = 0; r < (HOIST_WM ? NBW : 0); ++r) {
+        const int b = snake_block(r, warp, nb16);
+#pragma unroll
+        for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+            for (int kb = 0; kb < KP / 4; ++kb)
+                wm[r][mf][kb] = (r < nmy && b >= 0) ? __ldg(ly.W_m + ((size_t)(2 * b + mf) * (KP / 4) + kb) * 32 + lane) : 0.0;
+    }
     double acc[NBW][2][NF][2];
     for (int j = 0; j < total; ++j) {
         const int ti = j / (K + 1), s = j - ti * (K + 1), buf = j % NBUF;
         const double* T = Tb + (size_t)buf * tile_elems;
         const double* mb = mub + (size_t)(ti & 1) * NT * KP;
         const double* vb = vbs + (size_t)(ti & 1) * NT * KP;
-        if (!PROD_WARP && (j % SK_WARPS) == warp) {   // rotating producer duty: refill the buffer stage j - 1 used
-            const int jn = j + NBUF - 1;
-            if (jn >= NBUF && jn < total && lane == 0) issue(jn);
-            __syncwarp();
-        }
         mbar_wait(&full[buf], (unsigned)((j / NBUF) & 1));
         if (s == 0) {
 #pragma unroll
@@ -561,7 +569,8 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
                 for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
                     for (int kb = 0; kb < KP / 4; ++kb) {
-                        const double a = __ldg(ly.W_m + ((size_t)(2 * b + mf) * (KP / 4) + kb) * 32 + lane);
+                        const double a = HOIST_WM ? wm[HOIST_WM ? r : 0][mf][kb]
+                                                  : __ldg(ly.W_m + ((size_t)(2 * b + mf) * (KP / 4) + kb) * 32 + lane);
 #pragma unroll
                         for (int nf = 0; nf < NF; ++nf) dmma(acc[r][mf][nf], a, bm[kb][nf]);
                     }
@@ -577,7 +586,21 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&done[buf]);
+        if (lane == 0) {
+            if (PROD_WARP) {
+                mbar_arrive(&done[buf]);
+            } else {
+                // no producer warp: the LAST warp to leave the stage refills its buffer with stage j + NBUF at once —
+                // nobody waits for the stragglers (a rotating duty that waited on `done` cost 3.3 % of the kernel)
+                __threadfence_block();
+                const unsigned before = atomicAdd(&left[buf], 1u);
+                if (before == SK_WARPS - 1) {
+                    left[buf] = 0u;
+                    __threadfence_block();
+                    if (j + NBUF < total) issue(j + NBUF);
+                }
+            }
+        }
     }
 }
 

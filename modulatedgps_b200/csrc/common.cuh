@@ -39,6 +39,25 @@ __device__ __forceinline__ double sum_over_g(double v) {
     return v;
 }
 
+// Sums of 8 per-lane values over the 8 "g" groups with 7 shuffles instead of 24: at each butterfly level a lane hands
+// over the half of the values it will not keep.  Lane (g, t) returns the total of v[g] over all g' (same t).
+__device__ __forceinline__ double reduce8_over_g(const double (&v)[8], int lane) {
+    const bool b2 = (lane >> 4) & 1, b1 = (lane >> 3) & 1, b0 = (lane >> 2) & 1;
+    double w[4], x[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double keep = b2 ? v[i + 4] : v[i], send = b2 ? v[i] : v[i + 4];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double keep = b1 ? w[i + 2] : w[i], send = b1 ? w[i] : w[i + 2];
+        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const double keep = b0 ? x[1] : x[0], send = b0 ? x[0] : x[1];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 4);
+}
+
 // sum over the 4 "t" lanes of a group: xor 1, 2
 __device__ __forceinline__ double sum_over_t(double v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);

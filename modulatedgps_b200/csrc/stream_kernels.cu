@@ -402,30 +402,45 @@ __global__ void __launch_bounds__(SK_CTHREADS + 32, 1) cond_fwd_b_kernel(LayerDe
                         colsq[nf][1] = fma(acc[mf][nf][1], acc[mf][nf][1], colsq[nf][1]);
                     }
             }
+            if (NF == 4) {   // 8 values per lane: butterfly with hand-over (7 shuffles), lane (g, t) ends with column
+                             // (g >> 1) * 8 + 2 t + (g & 1) — every lane stores one distinct column
+                double v[8];
 #pragma unroll
-            for (int nf = 0; nf < NF; ++nf)
+                for (int nf = 0; nf < 4; ++nf) { v[2 * nf] = colsq[nf < NF ? nf : 0][0]; v[2 * nf + 1] = colsq[nf < NF ? nf : 0][1]; }
+                sq[(size_t)k * NT + (g >> 1) * 8 + 2 * t + (g & 1)] = reduce8_over_g(v, lane);
+            } else {
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const double s = sum_over_g(colsq[nf][e]);
-                    if (g == 0) sq[(size_t)k * NT + nf * 8 + 2 * t + e] = s;
-                }
+                for (int nf = 0; nf < NF; ++nf)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const double s = sum_over_g(colsq[nf][e]);
+                        if (g == 0) sq[(size_t)k * NT + nf * 8 + 2 * t + e] = s;
+                    }
+            }
         }
-        {   // this warp's slice of fmean^T [K x NT] = q_mu^T [K x Mp] * A tile   (rows >= K of W_mT are zero)
-            double acc[NF][2];
-#pragma unroll
-            for (int nf = 0; nf < NF; ++nf) acc[nf][0] = acc[nf][1] = 0.0;
+        {   // this warp's slice of fmean^T [K x NT] = q_mu^T [K x Mp] * A tile   (rows >= K of W_mT are zero).
+            // Two accumulator sets (even / odd k4-blocks): the contraction is a short dependent DMMA chain.
+            double acc[2][NF][2];
+            zero_acc<NF>(acc);
             const double* wm = ly.W_mT + (size_t)mkb0 * 32 + lane;
             const double* tb = T + t * STR + g;
-            for (int kb = mkb0; kb < mkb1; ++kb) {
-                const double a = __ldg(wm + (size_t)(kb - mkb0) * 32);
-                const double* tr = tb + (size_t)kb * 4 * STR;
+            for (int kb = mkb0; kb < mkb1; kb += 2) {   // (mkb1 - mkb0) = Mp / 32 ... a multiple of 2 when Mp % 64 == 0
+                const double a0 = __ldg(wm + (size_t)(kb - mkb0) * 32);
+                const double* tr0 = tb + (size_t)kb * 4 * STR;
 #pragma unroll
-                for (int nf = 0; nf < NF; ++nf) dmma(acc[nf], a, tr[nf * 8]);
+                for (int nf = 0; nf < NF; ++nf) dmma(acc[0][nf], a0, tr0[nf * 8]);
+                if (kb + 1 < mkb1) {
+                    const double a1 = __ldg(wm + (size_t)(kb + 1 - mkb0) * 32);
+                    const double* tr1 = tb + (size_t)(kb + 1) * 4 * STR;
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf) dmma(acc[1][nf], a1, tr1[nf * 8]);
+                }
             }
             if (g < K) {
 #pragma unroll
                 for (int nf = 0; nf < NF; ++nf)
-                    *reinterpret_cast<double2*>(mn + (size_t)g * NT + nf * 8 + 2 * t) = make_double2(acc[nf][0], acc[nf][1]);
+                    *reinterpret_cast<double2*>(mn + (size_t)g * NT + nf * 8 + 2 * t) =
+                        make_double2(acc[0][nf][0] + acc[1][nf][0], acc[0][nf][1] + acc[1][nf][1]);
             }
         }
         __syncwarp();

@@ -17,6 +17,7 @@ struct LayerDev {
     double* Zs_rm;    // [Mp, Dp]   rm   Z / lengthscales, 0 on padding
     double* Zs_fm;    // [Mp, Dp]   fm   same, left operand of the r^2 contraction
     double* zs2;      // [Mp]            |Zs_i|^2
+    double* zh;       // [Mp]            log(variance) - |Zs_i|^2 / 2  (row term of the Kuf exponent)
     double* Kuu;      // [Mp, Mp]   rm   k(Z,Z) + jitter I   (identity on padding)
     double* L;        // [Mp, Mp]   rm   chol(Kuu), strict upper = 0
     double* Linv;     // [Mp, Mp]   rm   L^-1

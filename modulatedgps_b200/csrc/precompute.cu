@@ -37,6 +37,7 @@ __global__ void prep_z_kernel(LayerDev ly) {
             s += v * v;
         }
         ly.zs2[i] = s;
+        ly.zh[i] = log(ly.variance[0]) - 0.5 * s;
     }
 }
 

@@ -25,9 +25,33 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "exp_tab.h"
 #include "kernels.h"
 
 namespace mgp {
+
+// exp(x) from a 64-entry table of 2^(j/64) and a degree-5 polynomial on |r| <= ln2/128: 10 FP64 instructions instead
+// of libdevice's 16-18, at most ~1 ulp from it (tools/gen_exp_tab.py).  It matters out of proportion to its pipe time:
+// in the two-CTA kernels a scalar FP64 instruction waits behind the other CTA's 16-clock DMMAs (~30 clocks each,
+// measured), so the Kuf generation phase is as long as its FP64 instruction count.  `tab` is the shared-memory copy.
+__device__ const double d_exp_tab64[64] = {EXP_TAB64_VALUES};
+__device__ __forceinline__ double exp_tab(double x, const double* tab) {
+    const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to the nearest integer in the low word
+    const double tt = fma(x, EXP_TAB_L, MAGIC);
+    const int k = __double2loint(tt);
+    const double kf = tt - MAGIC;
+    double r = fma(kf, -EXP_TAB_C_HI, x);
+    r = fma(kf, -EXP_TAB_C_LO, r);
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p *= r;
+    const double tj = tab[k & 63];
+    const double res = fma(tj, p, tj);
+    const double scaled = __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
+    return x < -700.0 ? 0.0 : scaled;   // (results below 1e-304 are flushed; the exponent add would leave the normal range)
+}
 
 constexpr int SK_WARPS = 8;                    // DMMA consumer warps
 constexpr int SK_CTHREADS = SK_WARPS * 32;
@@ -181,7 +205,8 @@ struct WPair {
     }
 };
 
-// Xs[n][d] = X[n0+n][d] / lengthscale_d (0 outside the chunk / padding); xs2[n] = |Xs_n|^2.  One warp.
+// Xs[n][d] = X[n0+n][d] / lengthscale_d (0 outside the chunk / padding); xs2[n] = -|Xs_n|^2 / 2 (column term of the
+// Kuf exponent).  One warp.
 template <int NT>
 __device__ __forceinline__ void stage_x_warp(const LayerDev& ly, const ChunkBuffers& cb, int64_t n0, double* Xs,
                                              double* xs2, int lane) {
@@ -196,16 +221,19 @@ __device__ __forceinline__ void stage_x_warp(const LayerDev& ly, const ChunkBuff
     for (int n = lane; n < NT; n += 32) {
         double s = 0.0;
         for (int d = 0; d < Dp; ++d) s += Xs[n * XSTR + d] * Xs[n * XSTR + d];
-        xs2[n] = s;
+        xs2[n] = -0.5 * s;
     }
     __syncwarp();
 }
 
 // Kuf values of the 8-row block rb8 in C-fragment layout: kv[nf][e] = k(z_{8 rb8+g}, x_{nf*8+2t+e}).
-// The -2 Zs.Xs contraction runs on DMMA (north_star: "squared-distance term on FP64 DMMA").
+// K = variance exp(-r2 / 2), r2 = -2 zs.xs + (|zs|^2 + |xs|^2)  (gpflow square_distance + K_r2) is evaluated as
+// exp(zs.xs + (log variance - |zs|^2/2) + (-|xs|^2/2)): the same cancellation as the reference's r2, two FP64
+// instructions instead of four around the exponential.  The zs.xs contraction runs on DMMA (north_star:
+// "squared-distance term on FP64 DMMA").  `etab`: shared-memory copy of d_exp_tab64.
 template <int NT>
 __device__ __forceinline__ void gen_kuf_block(const LayerDev& ly, int rb8, const double* Xs, const double* xs2,
-                                              double variance, double (&kv)[NT / 8][2], int lane) {
+                                              const double* etab, double (&kv)[NT / 8][2], int lane) {
     constexpr int NF = NT / 8;
     const int g = lane >> 2, t = lane & 3;
     const int Dp = ly.Dp, XSTR = xs_stride(Dp), D4 = Dp >> 2;
@@ -217,14 +245,14 @@ __device__ __forceinline__ void gen_kuf_block(const LayerDev& ly, int rb8, const
         for (int nf = 0; nf < NF; ++nf) dmma(kv[nf], a, Xs[(nf * 8 + g) * XSTR + kd * 4 + t]);
     }
     const int i = rb8 * 8 + g;
-    const double zi = __ldg(ly.zs2 + i);
+    const double zh = __ldg(ly.zh + i);
     const bool live = i < ly.M;
 #pragma unroll
     for (int nf = 0; nf < NF; ++nf)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-            const double r2 = -2.0 * kv[nf][e] + (zi + xs2[nf * 8 + 2 * t + e]);   // square_distance(X, X2)
-            kv[nf][e] = live ? variance * exp(-0.5 * r2) : 0.0;                    // K_r2
+            const double arg = kv[nf][e] + (zh + xs2[nf * 8 + 2 * t + e]);
+            kv[nf][e] = live ? exp_tab(arg, etab) : 0.0;
         }
 }
 
@@ -253,7 +281,8 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_fwd_a_kernel(LayerDev ly, Ch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nb16 = Mp / 16, nb8 = Mp / 8, C4 = Mp / 4;
     const size_t tile_elems = (size_t)Mp * STR;
-    const double variance = ly.variance[0];
+    __shared__ double etab[64];
+    if (threadIdx.x < 64) etab[threadIdx.x] = d_exp_tab64[threadIdx.x];   // visible after the first CTA barrier below
     const int nmy = my_block_count(warp, nb16);
     auto seg_of = [&](int i) { const int b = snake_block(i, warp, nb16); return Seg{ly.W_Linv, 2 * b, 0}; };
     WFrag wf;
@@ -266,7 +295,7 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_fwd_a_kernel(LayerDev ly, Ch
         __syncthreads();
         for (int rb = warp; rb < nb8; rb += SK_WARPS) {
             double kv[NF][2];
-            gen_kuf_block<NT>(ly, rb, Xs, xs2, variance, kv, lane);
+            gen_kuf_block<NT>(ly, rb, Xs, xs2, etab, kv, lane);
 #pragma unroll
             for (int nf = 0; nf < NF; ++nf)
                 *reinterpret_cast<double2*>(T + (size_t)(rb * 8 + g) * STR + nf * 8 + 2 * t) = make_double2(kv[nf][0], kv[nf][1]);
@@ -639,7 +668,8 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_bwd_b_kernel(LayerDev ly, Ch
     const int nb16 = Mp / 16, C4 = Mp / 4;
     const size_t tile_elems = (size_t)Mp * STR;
     const unsigned tile_bytes = (unsigned)(tile_elems * sizeof(double));
-    const double variance = ly.variance[0];
+    __shared__ double etab[64];
+    if (threadIdx.x < 64) etab[threadIdx.x] = d_exp_tab64[threadIdx.x];   // visible after the barrier-init sync below
     double* my_part = esum_part + (size_t)blockIdx.x * Mp * E;
     const int nmy = my_block_count(warp, nb16);
     auto seg_of = [&](int i) { const int b = snake_block(i, warp, nb16); return Seg{ly.W_LinvT, 2 * b, 4 * b}; };
@@ -680,7 +710,7 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_bwd_b_kernel(LayerDev ly, Ch
 #pragma unroll
             for (int mf = 0; mf < 2; ++mf) {
                 double kv[NF][2];
-                gen_kuf_block<NT>(ly, 2 * b + mf, Xs, xs2, variance, kv, lane);
+                gen_kuf_block<NT>(ly, 2 * b + mf, Xs, xs2, etab, kv, lane);
                 double e0 = 0.0;
 #pragma unroll
                 for (int nf = 0; nf < NF; ++nf)

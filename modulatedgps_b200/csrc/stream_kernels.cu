@@ -102,8 +102,15 @@ __device__ __forceinline__ void wfrag_load(WFrag& f, const Seg& sg, int C4, int 
 // first group of `cur`; on exit it holds the first group of `nxt`.
 // Groups are processed in PAIRS with two fragment register sets in ping-pong (no register copies on the loop
 // back-edge); tools/wloop_bench.cu: 35.0 vs 32.6 TFLOP/s for the copy-based loop at 8 warps per SM.
-template <int NT>
-__device__ __forceinline__ void wgemm_group(const WFrag& f, const double* tb, int kb, double (&acc)[2][NT / 8][2]) {
+// TRI says which fragments of a DIAGONAL group (the 16 x 16 block on the diagonal of a triangular left operand) are
+// identically zero and skipped: TRI_LOWER — rows 0-7 x columns 8-15 (first row block, k4-blocks 2, 3); TRI_UPPER — rows
+// 8-15 x columns 0-7 (second row block, k4-blocks 0, 1).  2 of the 8 (row block, k4-block) DMMA sets of that group, i.e.
+// 32 of the 1088 sets of a 256-row triangular operand: executed / algorithmic work 17/16 -> 33/32.  `diag` is
+// warp-uniform; the skipped DMMAs are predicated off (no pipe time).
+constexpr int TRI_NONE = 0, TRI_LOWER = 1, TRI_UPPER = 2;
+template <int NT, int TRI = TRI_NONE>
+__device__ __forceinline__ void wgemm_group(const WFrag& f, const double* tb, int kb, double (&acc)[2][NT / 8][2],
+                                            bool diag = false) {
     constexpr int NF = NT / 8, STR = NT + 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -111,12 +118,15 @@ __device__ __forceinline__ void wgemm_group(const WFrag& f, const double* tb, in
 #pragma unroll
         for (int nf = 0; nf < NF; ++nf) {
             const double b = tr[nf * 8];
-            dmma(acc[0][nf], f.a0[j], b);
-            dmma(acc[1][nf], f.a1[j], b);
+            if (TRI == TRI_LOWER && j >= 2) { if (!diag) dmma(acc[0][nf], f.a0[j], b); }
+            else dmma(acc[0][nf], f.a0[j], b);
+            if (TRI == TRI_UPPER && j < 2) { if (!diag) dmma(acc[1][nf], f.a1[j], b); }
+            else dmma(acc[1][nf], f.a1[j], b);
         }
     }
 }
-template <int NT>
+// TRI_LOWER: the segment ENDS with the diagonal group; TRI_UPPER: it STARTS with it.
+template <int NT, int TRI = TRI_NONE>
 __device__ __forceinline__ void wgemm_seg(const Seg& cur, int kb1, int C4, const double* Tsm, double (&acc)[2][NT / 8][2],
                                           int lane, WFrag& f, const Seg& nxt) {
     constexpr int STR = NT + 4;
@@ -137,15 +147,15 @@ __device__ __forceinline__ void wgemm_seg(const Seg& cur, int kb1, int C4, const
     WFrag n;
     if (((kb1 - kb) >> 2) & 1) {   // odd number of groups: one single step first
         load(n, (kb + 4 < kb1) ? wc + (size_t)(kb + 4) * 32 : wn);
-        wgemm_group<NT>(f, tb, kb, acc);
+        wgemm_group<NT, TRI>(f, tb, kb, acc, TRI == TRI_UPPER || kb + 4 == kb1);
         f = n;
         kb += 4;
     }
     for (; kb < kb1; kb += 8) {
         load(n, wc + (size_t)(kb + 4) * 32);
-        wgemm_group<NT>(f, tb, kb, acc);
+        wgemm_group<NT, TRI == TRI_UPPER ? TRI_UPPER : TRI_NONE>(f, tb, kb, acc, kb == cur.kb0);
         load(f, (kb + 8 < kb1) ? wc + (size_t)(kb + 8) * 32 : wn);
-        wgemm_group<NT>(n, tb, kb + 4, acc);
+        wgemm_group<NT, TRI == TRI_LOWER ? TRI_LOWER : TRI_NONE>(n, tb, kb + 4, acc, kb + 8 == kb1);
     }
 }
 
@@ -154,7 +164,7 @@ __device__ __forceinline__ void wgemm_seg(const Seg& cur, int kb1, int C4, const
 // exit, the first group of `nxt` sits in `b` (odd number of groups: the sets have swapped roles) and false if it
 // sits in `a` — there is NO register copy: after a copy-based odd step every DMMA of the next group waited for the
 // loads the copy had to wait for.  Callers keep both sets alive and alternate the argument order (WPair::run).
-template <int NT>
+template <int NT, int TRI = TRI_NONE>
 __device__ __forceinline__ bool wgemm_seg_sw(const Seg& cur, int kb1, int C4, const double* Tsm, double (&acc)[2][NT / 8][2],
                                           int lane, WFrag& a, WFrag& b, const Seg& nxt) {
     constexpr int STR = NT + 4;
@@ -176,20 +186,20 @@ __device__ __forceinline__ bool wgemm_seg_sw(const Seg& cur, int kb1, int C4, co
     if (!odd) {
         for (; kb < kb1; kb += 8) {
             load(b, wc + (size_t)(kb + 4) * 32);
-            wgemm_group<NT>(a, tb, kb, acc);
+            wgemm_group<NT, TRI == TRI_UPPER ? TRI_UPPER : TRI_NONE>(a, tb, kb, acc, kb == cur.kb0);
             load(a, (kb + 8 < kb1) ? wc + (size_t)(kb + 8) * 32 : wn);
-            wgemm_group<NT>(b, tb, kb + 4, acc);
+            wgemm_group<NT, TRI == TRI_LOWER ? TRI_LOWER : TRI_NONE>(b, tb, kb + 4, acc, kb + 8 == kb1);
         }
         return false;
     }
     load(b, (kb + 4 < kb1) ? wc + (size_t)(kb + 4) * 32 : wn);
-    wgemm_group<NT>(a, tb, kb, acc);
+    wgemm_group<NT, TRI>(a, tb, kb, acc, TRI == TRI_UPPER || kb + 4 == kb1);
     kb += 4;
     for (; kb < kb1; kb += 8) {   // roles swapped: b is current
         load(a, wc + (size_t)(kb + 4) * 32);
         wgemm_group<NT>(b, tb, kb, acc);
         load(b, (kb + 8 < kb1) ? wc + (size_t)(kb + 8) * 32 : wn);
-        wgemm_group<NT>(a, tb, kb + 4, acc);
+        wgemm_group<NT, TRI == TRI_LOWER ? TRI_LOWER : TRI_NONE>(a, tb, kb + 4, acc, kb + 8 == kb1);
     }
     return true;
 }
@@ -197,11 +207,11 @@ __device__ __forceinline__ bool wgemm_seg_sw(const Seg& cur, int kb1, int C4, co
 struct WPair {
     WFrag f, n;
     bool sw = false;
-    template <int NT>
+    template <int NT, int TRI = TRI_NONE>
     __device__ __forceinline__ void run(const Seg& cur, int kb1, int C4, const double* Tsm, double (&acc)[2][NT / 8][2],
                                         int lane, const Seg& nxt) {
-        if (!sw) { if (wgemm_seg_sw<NT>(cur, kb1, C4, Tsm, acc, lane, f, n, nxt)) sw = true; }
-        else { if (wgemm_seg_sw<NT>(cur, kb1, C4, Tsm, acc, lane, n, f, nxt)) sw = false; }
+        if (!sw) { if (wgemm_seg_sw<NT, TRI>(cur, kb1, C4, Tsm, acc, lane, f, n, nxt)) sw = true; }
+        else { if (wgemm_seg_sw<NT, TRI>(cur, kb1, C4, Tsm, acc, lane, n, f, nxt)) sw = false; }
     }
 };
 
@@ -305,6 +315,7 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_fwd_a_kernel(LayerDev ly, Ch
             const int b = snake_block(i, warp, nb16);
             double acc[2][NF][2];
             zero_acc<NF>(acc);
+            // (TRI_LOWER measured slower here, 5.78 vs 5.66 ms at config #4: the two CTAs' phases drift apart)
             wgemm_seg<NT>(seg_of(i), (b + 1) * 4, C4, T, acc, lane, wf, seg_of(i + 1 < nmy ? i + 1 : 0));   // lower triangular
 #pragma unroll
             for (int mf = 0; mf < 2; ++mf)
@@ -419,7 +430,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + 32, 1) cond_fwd_b_kernel(LayerDe
                 double acc[2][NF][2];
                 zero_acc<NF>(acc);
                 const Seg nxt = (r + 1 < nmy) ? seg_of(k, r + 1) : seg_of(k + 1 < K ? k + 1 : 0, 0);
-                wp.template run<NT>(seg_of(k, r), C4, C4, T, acc, lane, nxt);   // upper triangular
+                wp.template run<NT, TRI_UPPER>(seg_of(k, r), C4, C4, T, acc, lane, nxt);   // upper triangular
 #pragma unroll
                 for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
@@ -579,7 +590,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
                 double ck[2][NF][2];
                 zero_acc<NF>(ck);
                 const Seg nxt = (r + 1 < nmy) ? seg_of(s, r + 1) : seg_of(s + 1 < K ? s + 1 : 0, 0);
-                wgemm_seg<NT>(seg_of(s, r), (b + 1) * 4, C4, T, ck, lane, wf, nxt);   // lower triangular
+                wgemm_seg<NT, TRI_LOWER>(seg_of(s, r), (b + 1) * 4, C4, T, ck, lane, wf, nxt);   // lower triangular
 #pragma unroll
                 for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
@@ -705,7 +716,7 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_bwd_b_kernel(LayerDev ly, Ch
             const int b = snake_block(i, warp, nb16);
             double acc[2][NF][2];
             zero_acc<NF>(acc);
-            wgemm_seg<NT>(seg_of(i), C4, C4, T, acc, lane, wf, seg_of(i + 1 < nmy ? i + 1 : 0));   // upper triangular
+            wgemm_seg<NT, TRI_UPPER>(seg_of(i), C4, C4, T, acc, lane, wf, seg_of(i + 1 < nmy ? i + 1 : 0));   // upper triangular
             if (i == nmy - 1) { __syncwarp(); if (lane == 0) mbar_arrive(tfree); }   // this warp is done with T
 #pragma unroll
             for (int mf = 0; mf < 2; ++mf) {

@@ -122,14 +122,14 @@ __device__ __forceinline__ double robustmax_prob(int c, const double (&mu)[K], c
 // relaxed one-hot weights for one sample: W = exp(log_softmax((gumbel + logits)/T))
 template <int K>
 __device__ __forceinline__ void sample_weights(const double (&mu_a)[K], const double (&sd_a)[K], const double (&z)[K],
-                                               const double (&u)[K], double temperature, double (&W)[K]) {
+                                               const double (&u)[K], double inv_temperature, double (&W)[K]) {
     double x[K];
     double mx = -DBL_MAX;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const double logit = mu_a[k] + z[k] * sd_a[k];          // reparameterize: mean + z * (var + jitter)**0.5
         const double gumbel = -log(-log(u[k]));
-        x[k] = (gumbel + logit) / temperature;
+        x[k] = (gumbel + logit) * inv_temperature;   // (TFP divides: <= 1 ulp apart in x, ~1e-14 relative in W)
         mx = fmax(mx, x[k]);
     }
     // exp(log_softmax(x))_k = exp(x_k - mx) / sum_j exp(x_j - mx): the K exponentials are formed once and normalised
@@ -152,9 +152,11 @@ struct OnlineTerm {
 #pragma unroll
         for (int k = 0; k < K; ++k) mu[k] = v[k] = e[k] = 0.0;
     }
-    // one sample: weights W, per-component values c (t = sum_k W_k c_k), the normal draw z, sd = sqrt(var + jitter)
+    // one sample: weights W, per-component values c (t = sum_k W_k c_k), the normal draw z, hisd = 0.5 / sqrt(var + jitter)
+    // (the divisions by the temperature and by sd are loop-invariant: one reciprocal each, outside the sample loop —
+    // an FP64 division is ~25 instructions on the pipe this pass is bound by in throughput mode)
     __device__ __forceinline__ void add(const double (&W)[K], const double (&c)[K], const double (&z)[K],
-                                        const double (&sd)[K], double temperature) {
+                                        const double (&hisd)[K], double inv_temperature) {
         double t = 0.0;
 #pragma unroll
         for (int k = 0; k < K; ++k) t += W[k] * c[k];
@@ -172,9 +174,9 @@ struct OnlineTerm {
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const double xb = w * (c[k] * W[k] - W[k] * t) / temperature;   // d/d logits_k (up to 1/(s n))
+            const double xb = w * (c[k] * W[k] - W[k] * t) * inv_temperature;   // d/d logits_k (up to 1/(s n))
             mu[k] += xb;
-            v[k] += xb * z[k] * (0.5 / sd[k]);
+            v[k] += xb * z[k] * hisd[k];
             e[k] += w * W[k];
         }
     }
@@ -243,12 +245,16 @@ __global__ void __launch_bounds__(MC_THREADS) mc_pass_kernel(McArgs a, double* b
         //   w_s = exp(t_s - lse) / n_global ;  d/dW_k = w_s c_k ;  through exp(log_softmax(x)):
         //   xbar_k = Wbar_k W_k - W_k sum_j Wbar_j W_j = w_s (c_k W_k - W_k t_s)          (c = e or eA, t = sum_k W_k c_k)
         OnlineTerm<K> ty_acc, tA_acc;
+        const double inv_temperature = 1.0 / a.temperature;
+        double hisd_a[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) hisd_a[k] = 0.5 / sd_a[k];
         for (int s = 0; s < a.S; ++s) {
             double z[K], u[K], W[K];
             load_noise<K>(a, i, s, z, u);
-            sample_weights<K>(mu_a, sd_a, z, u, a.temperature, W);
-            ty_acc.add(W, e, z, sd_a, a.temperature);
-            if (MODEL == 1) tA_acc.add(W, eA, z, sd_a, a.temperature);
+            sample_weights<K>(mu_a, sd_a, z, u, inv_temperature, W);
+            ty_acc.add(W, e, z, hisd_a, inv_temperature);
+            if (MODEL == 1) tA_acc.add(W, eA, z, hisd_a, inv_temperature);
         }
         const double logS = log((double)a.S);
         const double lse_y = log(ty_acc.s) + ty_acc.m;
@@ -465,7 +471,7 @@ __global__ void predict_samples_k(SampleArgs a) {
             philox_draw(a.seed, a.point_offset + i, s, k, 1, zp[k], dummy);
         }
     }
-    sample_weights<K>(mu_a, sd_a, z, u, a.temperature, W);
+    sample_weights<K>(mu_a, sd_a, z, u, 1.0 / a.temperature, W);
     double mu[K], v[K], my[K], vy[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) { mu[k] = a.fmean_p[(size_t)i * K + k]; v[k] = a.fvar_p[(size_t)i * K + k]; }
@@ -525,7 +531,7 @@ __global__ void w_sample_k(SampleArgs a, double* W_out) {
             philox_draw(a.seed, a.point_offset + i, s, k, 0, z[k], u[k]);
         }
     }
-    sample_weights<K>(mu_a, sd_a, z, u, a.temperature, W);
+    sample_weights<K>(mu_a, sd_a, z, u, 1.0 / a.temperature, W);
 #pragma unroll
     for (int k = 0; k < K; ++k) W_out[idx * K + k] = W[k];
 }

@@ -26,7 +26,7 @@ struct Buf {
 
 struct LayerSlot {
     LayerDev dev{};
-    Buf inv_ls, Zs_rm, Zs_fm, zs2, zh, Kuu, L, Linv, W_Linv, W_LinvT, Lq_rm, W_LqT, Q_rm, W_Lq, W_m, W_mT, T1, T2, T3, Sfull, rowout;
+    Buf inv_ls, Zs_rm, Zs_fm, zs2, zh, Kuu, L, Linv, Dinv, W_Linv, W_LinvT, Lq_rm, W_LqT, Q_rm, W_Lq, W_m, W_mT, T1, T2, T3, Sfull, rowout;
     Buf A, Bk, fmean, fvar, mubar, vbar;   // chunk buffers
     Buf syrk_part, mraw_part, esum_part;    // per-CTA partial sums
     Buf syrk_plan;                          // SyrkWork[] of the current (Mp, K, chunk length)
@@ -167,18 +167,19 @@ int setup_layer(mgp_ctx* c, LayerSlot& s, const mgp_layer* l, bool need_bwd) {
     TRY(ensure(c, s.inv_ls, Dp * 8));
     TRY(ensure(c, s.Zs_rm, Mp * Dp * 8));
     TRY(ensure(c, s.Zs_fm, Mp * Dp * 8));
-    TRY(ensure(c, s.zs2, (2 * Mp + 16) * 8));
-    TRY(ensure(c, s.zh, Mp * 8));   // [Mp] |Zs_i|^2 + [Mp..] small scratch (KL partials)
+    TRY(ensure(c, s.zs2, (2 * Mp + 16) * 8));   // [Mp] |Zs_i|^2 + [Mp..] small scratch (KL partials)
+    TRY(ensure(c, s.zh, Mp * 8));
     TRY(ensure(c, s.Kuu, mm));
     TRY(ensure(c, s.L, mm));
     TRY(ensure(c, s.Linv, mm));
+    TRY(ensure(c, s.Dinv, Mp * 32 * 8));
     TRY(ensure(c, s.W_Linv, mm));
     TRY(ensure(c, s.W_LinvT, mm));
     TRY(ensure(c, s.Lq_rm, K * mm));
     TRY(ensure(c, s.W_LqT, K * mm));
     TRY(ensure(c, s.W_mT, 16 * Mp * 8));
     d.inv_ls = (double*)s.inv_ls.p; d.Zs_rm = (double*)s.Zs_rm.p; d.Zs_fm = (double*)s.Zs_fm.p; d.zs2 = (double*)s.zs2.p; d.zh = (double*)s.zh.p;
-    d.Kuu = (double*)s.Kuu.p; d.L = (double*)s.L.p; d.Linv = (double*)s.Linv.p;
+    d.Kuu = (double*)s.Kuu.p; d.L = (double*)s.L.p; d.Linv = (double*)s.Linv.p; d.Dinv = (double*)s.Dinv.p;
     d.W_Linv = (double*)s.W_Linv.p; d.W_LinvT = (double*)s.W_LinvT.p;
     d.Lq_rm = (double*)s.Lq_rm.p; d.W_LqT = (double*)s.W_LqT.p; d.W_mT = (double*)s.W_mT.p;
     if (need_bwd) {
@@ -384,7 +385,7 @@ void mgp_ctx_destroy(mgp_ctx* c) {
     cudaStreamSynchronize(c->stream);
     auto rel = [](Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; };
     for (auto& s : c->slot) {
-        Buf* all[] = {&s.inv_ls, &s.Zs_rm, &s.Zs_fm, &s.zs2, &s.zh, &s.Kuu, &s.L, &s.Linv, &s.W_Linv, &s.W_LinvT, &s.Lq_rm,
+        Buf* all[] = {&s.inv_ls, &s.Zs_rm, &s.Zs_fm, &s.zs2, &s.zh, &s.Kuu, &s.L, &s.Linv, &s.Dinv, &s.W_Linv, &s.W_LinvT, &s.Lq_rm,
                       &s.W_LqT, &s.Q_rm, &s.W_Lq, &s.W_m, &s.W_mT, &s.T1, &s.T2, &s.T3, &s.Sfull, &s.rowout, &s.A, &s.Bk,
                       &s.fmean, &s.fvar, &s.mubar, &s.vbar, &s.syrk_part, &s.mraw_part, &s.esum_part,
                       &s.syrk_plan};

@@ -21,6 +21,7 @@ struct LayerDev {
     double* Kuu;      // [Mp, Mp]   rm   k(Z,Z) + jitter I   (identity on padding)
     double* L;        // [Mp, Mp]   rm   chol(Kuu), strict upper = 0
     double* Linv;     // [Mp, Mp]   rm   L^-1
+    double* Dinv;     // [Mp/32][32][32] rm  inverses of the 32 x 32 diagonal blocks of L (chol_kernel -> trinv_kernel)
     double* W_Linv;   // [Mp, Mp]   fm   L^-1            (lower)
     double* W_LinvT;  // [Mp, Mp]   fm   L^-T            (upper)
     double* Lq_rm;    // [K, Mp, Mp] rm  tril(q_sqrt), zero padded

@@ -62,60 +62,95 @@ __global__ void kuu_kernel(LayerDev ly) {
 
 // --------------------------------------------------------------------------------------------------
 // Blocked right-looking Cholesky, one CTA per matrix (matrix stays in L2; 32-wide panels).
-//   (1) diagonal 32x32 block: one warp, one row per lane in registers, warp shuffles for the pivots
-//   (2) panel solve: one row per thread against the diagonal block held in shared memory
+//   (1) diagonal 32x32 block D: one warp, one row per lane in registers, warp shuffles for the pivots; the same warp
+//       then forms V = D^-1 (lane j owns column j, forward substitution against D in shared memory) and keeps it for
+//       the panel and for trinv_kernel (`Dinv`, [Mp/32][32][32])
+//   (2) panel: P <- P V^T on DMMA, one 8-row block per warp step (was: one row per thread, a 528-FMA dependent chain
+//       per row — the longest phase of a panel step)
 //   (3) trailing update on DMMA, one 32x32 tile per warp
+// The diagonal blocks' explicit inverses cost cond(D) eps <= cond(L) eps in the panel, the same order as the explicit
+// L^-1 every consumer of this factor uses anyway.
 // --------------------------------------------------------------------------------------------------
 constexpr int CHOL_THREADS = 512;
 
-__global__ void __launch_bounds__(CHOL_THREADS, 1) chol_kernel(double* L, int Mp, int* status) {
+__global__ void __launch_bounds__(CHOL_THREADS, 1) chol_kernel(double* L, double* Dinv, int Mp, int* status) {
     __shared__ double Dg[32][33];
+    __shared__ double Vg[32][36];   // row stride == 4 mod 16 doubles: conflict-free B-fragment reads
+    __shared__ double invd[32];     // 1 / D[r][r]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int nblk = Mp / 32;
     for (int jb = 0; jb < nblk; ++jb) {
         const int j0 = jb * 32;
         if (warp == 0) {
-            double row[32];
+            {
+                double row[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) row[c] = L[(size_t)(j0 + lane) * Mp + j0 + c];
+                for (int c = 0; c < 32; ++c) row[c] = L[(size_t)(j0 + lane) * Mp + j0 + c];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const double piv = __shfl_sync(0xffffffffu, row[c], c);
-                if (!(piv > 0.0) && lane == 0) atomicOr(status, 1);
-                const double d = sqrt(piv);
-                const double l = (lane == c) ? d : row[c] / d;
-                row[c] = l;
+                for (int c = 0; c < 32; ++c) {
+                    const double piv = __shfl_sync(0xffffffffu, row[c], c);
+                    if (!(piv > 0.0) && lane == 0) atomicOr(status, 1);
+                    // one reciprocal square root instead of sqrt + division on the pivot chain (both are ~20-instruction
+                    // sequences): d = piv * rsqrt(piv), l = row * rsqrt(piv), <= 2 ulp from the correctly rounded values
+                    const double ri = rsqrt(piv);
+                    const double l = (lane == c) ? piv * ri : row[c] * ri;
+                    if (lane == c) invd[c] = ri;
+                    row[c] = l;
 #pragma unroll
-                for (int cc = c + 1; cc < 32; ++cc) {
-                    const double lcc = __shfl_sync(0xffffffffu, l, cc);
-                    row[cc] -= l * lcc;
+                    for (int cc = c + 1; cc < 32; ++cc) {
+                        const double lcc = __shfl_sync(0xffffffffu, l, cc);
+                        row[cc] -= l * lcc;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const double v = (c <= lane) ? row[c] : 0.0;
+                    Dg[lane][c] = v;
+                    L[(size_t)(j0 + lane) * Mp + j0 + c] = v;
                 }
             }
+            __syncwarp();
+            {   // V = D^-1, column `lane`:  y_r = (delta_{r,lane} - sum_{q<r} D[r][q] y_q) / D[r][r]   (y_q = 0 for q < lane).
+                // Column-oriented: once y_q is final, every later row's sum takes its term — the dependent chain is one
+                // FMA + one multiply per row instead of a whole row sum + a division.
+                double y[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const double v = (c <= lane) ? row[c] : 0.0;
-                Dg[lane][c] = v;
-                L[(size_t)(j0 + lane) * Mp + j0 + c] = v;
+                for (int r = 0; r < 32; ++r) y[r] = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    y[q] *= invd[q];
+#pragma unroll
+                    for (int r = q + 1; r < 32; ++r) y[r] = fma(-Dg[r][q], y[q], y[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    Vg[r][lane] = y[r];
+                    Dinv[((size_t)j0 + r) * 32 + lane] = y[r];
+                }
             }
         }
         __syncthreads();
-        // volatile view: keeps the compiler from hoisting all 528 diagonal-block loads out of the row loop
-        const volatile double(*Dv)[33] = Dg;
-        for (int i = j0 + 32 + tid; i < Mp; i += CHOL_THREADS) {
-            double x[32];
-            double* rowp = L + (size_t)i * Mp + j0;
+        // panel rows i >= j0 + 32:  X[i][c] = sum_p P[i][p] V[c][p]
+        const int prow0 = j0 + 32;
+        for (int u = warp; u < (Mp - prow0) / 8; u += CHOL_THREADS / 32) {
+            double* rowp = L + (size_t)(prow0 + u * 8 + g) * Mp + j0;
+            double a[8];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) x[c] = rowp[c];
+            for (int kk = 0; kk < 8; ++kk) a[kk] = rowp[kk * 4 + t];
+            double acc[4][2];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                double s = x[c];
+            for (int ni = 0; ni < 4; ++ni) acc[ni][0] = acc[ni][1] = 0.0;
 #pragma unroll
-                for (int p = 0; p < c; ++p) s -= x[p] * Dv[c][p];
-                x[c] = s / Dv[c][c];
+            for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma(acc[ni], a[kk], Vg[ni * 8 + g][kk * 4 + t]);
+            __syncwarp();   // every lane of the warp has read its part of the 8 rows before they are overwritten
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+                rowp[ni * 8 + 2 * t] = acc[ni][0];
+                rowp[ni * 8 + 2 * t + 1] = acc[ni][1];
             }
-#pragma unroll
-            for (int c = 0; c < 32; ++c) rowp[c] = x[c];
         }
         __syncthreads();
         const int nb = nblk - jb - 1;
@@ -131,7 +166,7 @@ __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_kernel(double* L, int Mp
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-#pragma unroll 2
+#pragma unroll 4
             for (int kk = 0; kk < 8; ++kk) {
                 double a[4], b[4];
 #pragma unroll
@@ -161,45 +196,69 @@ __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_kernel(double* L, int Mp
 }
 
 // --------------------------------------------------------------------------------------------------
-// X = L^-1 by block forward substitution, one CTA per 32-column block of X (X pre-zeroed).
+// X = L^-1 by block forward substitution, one CTA per 32-column block of X (X pre-zeroed):
+//   X_ij = V_i (delta_ij I - sum_{j <= p < i} L_ip X_pj),   V_i = (L_ii)^-1 from chol_kernel.
+// The L_ip and X_pj blocks are staged through shared memory, the next pair fetched into registers while the current
+// one is multiplied (the scalar loop over global memory this replaces paid an L2 round trip per 4 columns).
 // --------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) trinv_kernel(const double* L, double* X, int Mp) {
-    __shared__ double Dii[32][33];
-    __shared__ double R[32][33];
+__global__ void __launch_bounds__(256) trinv_kernel(const double* L, const double* Dinv, double* X, int Mp) {
+    __shared__ double Ls[32][33];
+    __shared__ __align__(16) double Xs[32][36];
+    __shared__ __align__(16) double R[32][36];
+    __shared__ double Vs[32][33];
     const int jb = blockIdx.x, nblk = Mp / 32, tid = threadIdx.x;
     const int r = tid >> 3, c4 = (tid & 7) * 4;
     for (int ib = jb; ib < nblk; ++ib) {
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        const double* Lrow = L + (size_t)(ib * 32 + r) * Mp;
-        for (int p = jb * 32; p < ib * 32; ++p) {
-            const double l = Lrow[p];
-            const double* xr = X + (size_t)p * Mp + jb * 32 + c4;
-            acc[0] += l * xr[0];
-            acc[1] += l * xr[1];
-            acc[2] += l * xr[2];
-            acc[3] += l * xr[3];
+        double lreg[4], xreg[4];
+        auto fetch = [&](int pb) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int idx = tid + 256 * m, rr = idx >> 5, cc = idx & 31;
+                lreg[m] = L[(size_t)(ib * 32 + rr) * Mp + pb * 32 + cc];
+                xreg[m] = X[(size_t)(pb * 32 + rr) * Mp + jb * 32 + cc];
+            }
+        };
+        if (jb < ib) fetch(jb);
+        for (int pb = jb; pb < ib; ++pb) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int idx = tid + 256 * m, rr = idx >> 5, cc = idx & 31;
+                Ls[rr][cc] = lreg[m];
+                Xs[rr][cc] = xreg[m];
+            }
+            __syncthreads();
+            if (pb + 1 < ib) fetch(pb + 1);
+#pragma unroll 8
+            for (int p = 0; p < 32; ++p) {
+                const double l = Ls[r][p];
+                const double2 x01 = *reinterpret_cast<const double2*>(&Xs[p][c4]);
+                const double2 x23 = *reinterpret_cast<const double2*>(&Xs[p][c4 + 2]);
+                acc[0] = fma(l, x01.x, acc[0]);
+                acc[1] = fma(l, x01.y, acc[1]);
+                acc[2] = fma(l, x23.x, acc[2]);
+                acc[3] = fma(l, x23.y, acc[3]);
+            }
+            __syncthreads();
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) R[r][c4 + q] = ((ib == jb && r == c4 + q) ? 1.0 : 0.0) - acc[q];
-        for (int idx = tid; idx < 1024; idx += 256)
-            Dii[idx >> 5][idx & 31] = L[(size_t)(ib * 32 + (idx >> 5)) * Mp + ib * 32 + (idx & 31)];
+        for (int idx = tid; idx < 1024; idx += 256) Vs[idx >> 5][idx & 31] = Dinv[(size_t)ib * 1024 + idx];
         __syncthreads();
-        if (tid < 32) {
-            double y[32];
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr) {
-                double s = R[rr][tid];
-#pragma unroll
-                for (int q = 0; q < rr; ++q) s -= Dii[rr][q] * y[q];
-                y[rr] = s / Dii[rr][rr];
-            }
-#pragma unroll
-            for (int rr = 0; rr < 32; ++rr) R[rr][tid] = y[rr];
+        double o[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k <= r; ++k) {   // V_i is lower triangular
+            const double v = Vs[r][k];
+            const double2 r01 = *reinterpret_cast<const double2*>(&R[k][c4]);
+            const double2 r23 = *reinterpret_cast<const double2*>(&R[k][c4 + 2]);
+            o[0] = fma(v, r01.x, o[0]);
+            o[1] = fma(v, r01.y, o[1]);
+            o[2] = fma(v, r23.x, o[2]);
+            o[3] = fma(v, r23.y, o[3]);
         }
-        __syncthreads();
-        for (int idx = tid; idx < 1024; idx += 256)
-            X[(size_t)(ib * 32 + (idx >> 5)) * Mp + jb * 32 + (idx & 31)] = R[idx >> 5][idx & 31];
-        __syncthreads();
+        double* xo = X + (size_t)(ib * 32 + r) * Mp + jb * 32 + c4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xo[q] = o[q];
+        __syncthreads();   // the block just written is read (from global memory) by this CTA's later steps
     }
 }
 
@@ -258,9 +317,9 @@ void precompute_layer(const LayerDev& ly, bool need_bwd, int* d_status, const La
     kuu_kernel<<<(unsigned)((mm + 255) / 256), 256, 0, ln.stream>>>(ly);
     ln.tick(2);
     cudaMemcpyAsync(ly.L, ly.Kuu, sizeof(double) * mm, cudaMemcpyDeviceToDevice, ln.stream);
-    chol_kernel<<<1, CHOL_THREADS, 0, ln.stream>>>(ly.L, Mp, d_status);
+    chol_kernel<<<1, CHOL_THREADS, 0, ln.stream>>>(ly.L, ly.Dinv, Mp, d_status);
     cudaMemsetAsync(ly.Linv, 0, sizeof(double) * mm, ln.stream);
-    trinv_kernel<<<Mp / 32, 256, 0, ln.stream>>>(ly.L, ly.Linv, Mp);
+    trinv_kernel<<<Mp / 32, 256, 0, ln.stream>>>(ly.L, ly.Dinv, ly.Linv, Mp);
     ln.tick(2);
     pack_fm(ly.W_Linv, Mp, Mp, 0, Mp, ly.Linv, Mp, Mp, Mp, false, 1, 0, 0, ln);
     pack_fm(ly.W_LinvT, Mp, Mp, 0, Mp, ly.Linv, Mp, Mp, Mp, true, 1, 0, 0, ln);
@@ -289,9 +348,42 @@ __global__ void reduce_partials_kernel(double* dst, const double* src, int64_t n
     dst[i] = s;
 }
 
+// Many parts, few elements (the E-sums: one part per cond_bwd_b CTA, Mp (1 + 2 Dp) elements): a thread per element
+// would walk hundreds of strided loads one after another.  Here a CTA takes 32 elements x 8 part lanes; lane py sums
+// parts py, py + 8, ... and the 8 lane sums are added in a fixed order, so the result stays deterministic.
+__global__ void __launch_bounds__(256) reduce_partials_tall_kernel(double* dst, const double* src, int64_t n, int nparts,
+                                                                   int64_t stride, int accumulate) {
+    __shared__ double part[8][33];
+    const int ex = threadIdx.x & 31, py = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + ex;
+    double s0 = 0.0, s1 = 0.0;
+    if (i < n) {
+        int p = py;
+        for (; p + 8 < nparts; p += 16) {
+            s0 += src[(int64_t)p * stride + i];
+            s1 += src[(int64_t)(p + 8) * stride + i];
+        }
+        if (p < nparts) s0 += src[(int64_t)p * stride + i];
+    }
+    part[py][ex] = s0 + s1;
+    __syncthreads();
+    if (py == 0 && i < n) {
+        double s = accumulate ? dst[i] : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += part[q][ex];
+        dst[i] = s;
+    }
+}
+
 void reduce_partials(double* dst, const double* src, int64_t n, int nparts, int64_t stride, bool accumulate,
                      const Launch& ln) {
     if (n <= 0) return;
+    if (nparts >= 64 && n <= 65536) {
+        reduce_partials_tall_kernel<<<(unsigned)((n + 31) / 32), 256, 0, ln.stream>>>(dst, src, n, nparts, stride,
+                                                                                      accumulate ? 1 : 0);
+        ln.tick();
+        return;
+    }
     reduce_partials_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ln.stream>>>(dst, src, n, nparts, stride,
                                                                                accumulate ? 1 : 0);
     ln.tick();

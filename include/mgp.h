@@ -186,6 +186,11 @@ int mgp_adam_step(void* cuda_stream, const mgp_adam_slot* slots, int32_t nslots,
 int mgp_gather_rows(void* cuda_stream, const double* X, const double* Y, const int64_t* idx, int64_t B, int32_t D,
                     double* Xb, double* Yb);
 
+/* gpflow.utilities.triangular() — the TFP FillTriangular bijector behind SVGP.q_sqrt (gpflow/models/svgp.py, pinned
+ * 2.7.0): inverse == 0: src [batch, m(m+1)/2] -> dst [batch, m, m] (lower band, zeros above);
+ * inverse != 0: src [batch, m, m] -> dst [batch, m(m+1)/2] (also the adjoint: the map is a permutation). */
+int mgp_fill_triangular(void* cuda_stream, const double* src, int64_t batch, int32_t m, double* dst, int32_t inverse);
+
 /* `iters` Lloyd iterations from the given centroids [M, D] (in place), then labels int32 [N], cluster sizes int32 [M]
  * and the mean Euclidean distance to the nearest centroid (scipy.cluster.vq.kmeans' distortion; call site
  * demos/demo_tf2.py:39).  scratch: >= 592 doubles.  Empty clusters keep their centroid and report count 0. */

@@ -102,6 +102,7 @@ _PROTOTYPES = {
                                 C.c_double, C.c_double, C.c_int64]),
     "mgp_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                   C.c_void_p]),
+    "mgp_fill_triangular": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]),
     "mgp_kmeans_iterate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

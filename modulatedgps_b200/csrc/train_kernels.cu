@@ -51,6 +51,31 @@ __global__ void gather_rows_kernel(const double* X, const double* Y, const int64
     else Yb[r] = Y[src];
 }
 
+// ---- gpflow.utilities.triangular() = TFP FillTriangular ----------------------------------------
+// vector x of length n = m(m+1)/2  ->  concat([x[m:], reversed(x)]) reshaped [m, m], lower band.
+__device__ __forceinline__ int64_t fill_tri_src(int i, int j, int m, int64_t n) {
+    const int64_t t = (int64_t)i * m + j;
+    return t < n - m ? m + t : n - 1 - (t - (n - m));
+}
+// forward: every element of the [batch, m, m] output is written (zeros above the diagonal) — no separate fill
+__global__ void fill_tri_fwd_kernel(const double* x, int64_t batch, int m, double* out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t mm = (int64_t)m * m, n = (int64_t)m * (m + 1) / 2;
+    if (idx >= batch * mm) return;
+    const int64_t b = idx / mm;
+    const int r = (int)(idx - b * mm), i = r / m, j = r - i * m;
+    out[idx] = (j <= i) ? x[b * n + fill_tri_src(i, j, m, n)] : 0.0;
+}
+// inverse (also the adjoint of the forward map, it is a permutation of the lower triangle): x[src(i, j)] = mat[i][j]
+__global__ void fill_tri_inv_kernel(const double* mat, int64_t batch, int m, double* x) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t mm = (int64_t)m * m, n = (int64_t)m * (m + 1) / 2;
+    if (idx >= batch * mm) return;
+    const int64_t b = idx / mm;
+    const int r = (int)(idx - b * mm), i = r / m, j = r - i * m;
+    if (j <= i) x[b * n + fill_tri_src(i, j, m, n)] = mat[idx];
+}
+
 // ---- f4: k-means ----------------------------------------------------------------------------------------------
 // assignment: nearest centroid (squared Euclidean, lowest index wins ties); centroids staged in shared memory
 __global__ void __launch_bounds__(256) kmeans_assign_kernel(const double* X, int64_t N, int D, const double* C, int M,
@@ -136,6 +161,16 @@ int mgp_gather_rows(void* cuda_stream, const double* X, const double* Y, const i
     if (B == 0) return MGP_OK;
     const int64_t total = B * (D + 1);
     gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(X, Y, idx, B, D, Xb, Yb);
+    return cudaGetLastError() == cudaSuccess ? MGP_OK : MGP_ERR_CUDA;
+}
+
+int mgp_fill_triangular(void* cuda_stream, const double* src, int64_t batch, int32_t m, double* dst, int32_t inverse) {
+    if (batch < 0 || m < 1 || (batch > 0 && (!src || !dst))) return MGP_ERR_BAD_ARG;
+    if (batch == 0) return MGP_OK;
+    const int64_t total = batch * m * m;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (inverse) fill_tri_inv_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(src, batch, m, dst);
+    else fill_tri_fwd_kernel<<<grid, 256, 0, (cudaStream_t)cuda_stream>>>(src, batch, m, dst);
     return cudaGetLastError() == cudaSuccess ? MGP_OK : MGP_ERR_CUDA;
 }
 

@@ -178,7 +178,9 @@ class _ElboFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
-        return (None, None, None, None, None, None) + tuple(None if g is None else gout * g for g in ctx.grads)
+        live = [g for g in ctx.grads if g is not None]
+        scaled = iter(torch._foreach_mul(live, gout))        # one multi-tensor kernel instead of one launch per variable
+        return (None, None, None, None, None, None) + tuple(None if g is None else next(scaled) for g in ctx.grads)
 
 
 class _RelaxedAssignments:
@@ -444,7 +446,8 @@ class SMGP(SGP):
         def add(p, g):
             if p is None or not isinstance(p, Parameter):
                 return
-            g = g.reshape(p.value().shape) if g.numel() == p.value().numel() else g
+            shape = p.shape                      # (of the constrained value; evaluating p.value() here would re-run
+            g = g.reshape(shape) if g.numel() == shape.numel() else g   # the bijector kernels twice per parameter)
             out[id(p)] = (p, g if id(p) not in out else out[id(p)][1] + g)
 
         for lname, layer in (("pred", self.pred_layer), ("assign", self.assign_layer)):

@@ -55,6 +55,9 @@ class Identity:
     def grad_to_unconstrained(self, g_constrained, x_unconstrained):
         return g_constrained
 
+    def forward_shape(self, shape):
+        return tuple(shape)
+
 
 class Softplus:
     """gpflow.utilities.positive() with the default softplus bijector and zero lower bound."""
@@ -68,6 +71,9 @@ class Softplus:
 
     def grad_to_unconstrained(self, g_constrained, x_unconstrained):
         return g_constrained * torch.sigmoid(x_unconstrained)
+
+    def forward_shape(self, shape):
+        return tuple(shape)
 
 
 class FillTriangular:
@@ -87,9 +93,30 @@ class FillTriangular:
             self._cache[key] = (flat_pos, src)
         return self._cache[key]
 
+    @staticmethod
+    def _kernel(src, m, out, inverse):
+        """One libmgp launch (mgp_fill_triangular) for device tensors outside autograd: the index / index_put route
+        below costs three torch kernels per call, and the step evaluates this bijector four times."""
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load_library()
+        batch = src.numel() // (m * m if inverse else m * (m + 1) // 2)
+        rc = lib.mgp_fill_triangular(C.c_void_p(torch.cuda.current_stream(src.device).cuda_stream), _lib.ptr(src), batch, m,
+                                     _lib.ptr(out), 1 if inverse else 0)
+        if rc != 0:
+            raise _lib.MgpError(rc, "mgp_fill_triangular failed")
+        return out
+
+    @staticmethod
+    def _use_kernel(t):
+        return t.is_cuda and t.dtype == F64 and not (torch.is_grad_enabled() and t.requires_grad)
+
     def forward(self, x):
         n = x.shape[-1]
         m = int(round((np.sqrt(8 * n + 1) - 1) / 2))
+        if self._use_kernel(x):
+            out = torch.empty(*x.shape[:-1], m, m, dtype=x.dtype, device=x.device)
+            return self._kernel(x.contiguous(), m, out, False)
         flat_pos, src = self._maps(m, x.device)
         out = torch.zeros(*x.shape[:-1], m * m, dtype=x.dtype, device=x.device)
         out[..., flat_pos] = x[..., src]
@@ -97,6 +124,9 @@ class FillTriangular:
 
     def inverse(self, y):
         m = y.shape[-1]
+        if self._use_kernel(y):
+            out = torch.empty(*y.shape[:-2], m * (m + 1) // 2, dtype=y.dtype, device=y.device)
+            return self._kernel(y.contiguous(), m, out, True)
         flat_pos, src = self._maps(m, y.device)
         out = torch.zeros(*y.shape[:-2], m * (m + 1) // 2, dtype=y.dtype, device=y.device)
         out[..., src] = y.reshape(*y.shape[:-2], m * m)[..., flat_pos]
@@ -104,6 +134,11 @@ class FillTriangular:
 
     def grad_to_unconstrained(self, g_constrained, x_unconstrained):
         return self.inverse(g_constrained)
+
+    def forward_shape(self, shape):
+        n = shape[-1]
+        m = int(round((np.sqrt(8 * n + 1) - 1) / 2))
+        return tuple(shape[:-1]) + (m, m)
 
 
 class Parameter:
@@ -132,7 +167,8 @@ class Parameter:
 
     @property
     def shape(self):
-        return self.value().shape
+        """Shape of the constrained value (no kernel is launched to find it)."""
+        return torch.Size(self.transform.forward_shape(self.unconstrained_variable.shape))
 
 
 class Module:

@@ -428,3 +428,23 @@ def test_w_dist_and_e_log_p_y_match_the_oracle(model_kind, lik, hg):
     # rows of W are probability vectors; a Philox draw has the same shape
     assert np.abs(W.sum(-1).cpu().numpy() - 1.0).max() <= 1e-12
     assert tuple(model.W_dist(X).sample(2).shape) == (2, S * N, K)
+
+
+@pytest.mark.parametrize("m,batch", [(1, 1), (5, 2), (37, 3), (256, 4)])
+def test_fill_triangular_kernel_is_the_tfp_permutation(m, batch, hg):
+    """mgp_fill_triangular (forward and inverse/adjoint) against the index-map route checked on the CPU against the
+    TFP example (tests/test_host_logic.py) — bit-exact: it is a permutation."""
+    from modulatedgps_b200.parameter import FillTriangular, fill_triangular_index
+    ft = FillTriangular()
+    n = m * (m + 1) // 2
+    x = torch.randn(batch, n, dtype=torch.float64, device="cuda")
+    L_k = ft.forward(x)                                   # kernel route (CUDA tensor outside autograd)
+    idx = fill_triangular_index(m)
+    ref = np.zeros((batch, m, m))
+    ii, jj = np.nonzero(idx >= 0)
+    ref[:, ii, jj] = x.cpu().numpy()[:, idx[ii, jj]]
+    assert np.array_equal(L_k.cpu().numpy(), ref)
+    g = torch.randn(batch, m, m, dtype=torch.float64, device="cuda")
+    back = ft.inverse(g)
+    assert np.array_equal(back.cpu().numpy()[:, idx[ii, jj]], g.cpu().numpy()[:, ii, jj])
+    assert torch.equal(ft.inverse(L_k), x)

@@ -82,6 +82,8 @@ struct mgp_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;          // the assign layer's replicated work runs here, concurrently with the pred layer's
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t aux = nullptr;           // the q_mu / q_sqrt chains of both layers and the KL terms (independent of Kuu)
+    cudaEvent_t ev_fork_aux = nullptr, ev_join_aux = nullptr;
     int num_sms = 0;
     size_t total_mem = 0;
     int64_t launches = 0;
@@ -90,6 +92,7 @@ struct mgp_ctx {
     LayerSlot slot[2];
     Buf mc_part, scratch_rb, kl, status;
     bool pre_valid = false;
+    bool kl_valid = false;   // the KL terms in `kl` belong to the current precompute (formed by mgp_elbo_local)
     bool pick_valid = false;
     int64_t pick_key[5] = {0, 0, 0, 0, 0};
     int64_t pick_value = 0;
@@ -251,6 +254,15 @@ void join_side(mgp_ctx* c) {
     cudaEventRecord(c->ev_join, c->side);
     cudaStreamWaitEvent(c->stream, c->ev_join, 0);
 }
+Launch fork_aux(mgp_ctx* c) {
+    cudaEventRecord(c->ev_fork_aux, c->stream);
+    cudaStreamWaitEvent(c->aux, c->ev_fork_aux, 0);
+    return Launch{c->aux, &c->launches, c->num_sms};
+}
+void join_aux(mgp_ctx* c) {
+    cudaEventRecord(c->ev_join_aux, c->aux);
+    cudaStreamWaitEvent(c->stream, c->ev_join_aux, 0);
+}
 
 // host-side stall finder (MGP_HOST_PROFILE=1): prints any bracketed host section that takes longer than 2 ms
 struct HostTimer {
@@ -366,6 +378,9 @@ int mgp_ctx_create(int device, void* cuda_stream, mgp_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->total_mem = prop.totalGlobalMem;
     if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork_aux, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join_aux, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         delete c;
@@ -393,6 +408,9 @@ void mgp_ctx_destroy(mgp_ctx* c) {
     }
     rel(c->mc_part); rel(c->scratch_rb); rel(c->kl); rel(c->status);
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+    if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
+    if (c->ev_fork_aux) cudaEventDestroy(c->ev_fork_aux);
+    if (c->ev_join_aux) cudaEventDestroy(c->ev_join_aux);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
@@ -444,7 +462,7 @@ int mgp_svgp_predict_f(mgp_ctx* c, const mgp_layer* layer, const double* X, int6
     if (!c) return MGP_ERR_BAD_ARG;
     if (N < 0 || (N > 0 && (!X || !fmean || !fvar))) return fail(c, MGP_ERR_BAD_ARG, "predict_f: bad arguments");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    c->pre_valid = false;
+    c->pre_valid = false; c->kl_valid = false;
     TRY(setup_layer(c, c->slot[0], layer, false));
     if (N == 0) return MGP_OK;
     precompute_layer(c->slot[0].dev, false, (int*)c->status.p, launch_of(c));
@@ -457,7 +475,7 @@ int mgp_prior_kl(mgp_ctx* c, const mgp_layer* layer, double* kl) {
     if (!c) return MGP_ERR_BAD_ARG;
     if (!kl) return fail(c, MGP_ERR_BAD_ARG, "prior_kl: NULL output");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    c->pre_valid = false;
+    c->pre_valid = false; c->kl_valid = false;
     TRY(setup_layer(c, c->slot[0], layer, false));
     prior_kl_layer(c->slot[0].dev, kl, launch_of(c));
     CUDA_TRY(c, cudaGetLastError());
@@ -496,7 +514,7 @@ int mgp_predict_samples(mgp_ctx* c, const mgp_layer* pred, const mgp_layer* assi
     if (lik == MGP_LIK_GAUSSIAN && !lik_var) return fail(c, MGP_ERR_BAD_ARG, "predict_samples: needs lik_var");
     if (N == 0) return MGP_OK;
     CUDA_TRY(c, cudaSetDevice(c->device));
-    c->pre_valid = false;
+    c->pre_valid = false; c->kl_valid = false;
     TRY(check_layer(c, pred));
     TRY(check_layer(c, assign));
     if (pred->K != assign->K || pred->D != assign->D) return fail(c, MGP_ERR_BAD_ARG, "pred/assign layers disagree on K or D");
@@ -529,7 +547,7 @@ int mgp_w_sample(mgp_ctx* c, const mgp_layer* assign, const double* X, int64_t N
     if ((noise->z == nullptr) != (noise->u == nullptr)) return fail(c, MGP_ERR_BAD_ARG, "w_sample: z and u must be given together");
     if (N == 0) return MGP_OK;
     CUDA_TRY(c, cudaSetDevice(c->device));
-    c->pre_valid = false;
+    c->pre_valid = false; c->kl_valid = false;
     TRY(check_layer(c, assign));
     const int K = assign->K;
     TRY(ensure(c, c->scratch_rb, (size_t)N * K * 8 * 2));
@@ -557,7 +575,7 @@ int mgp_e_log_p_y(mgp_ctx* c, const mgp_layer* pred, int32_t lik, const double* 
     if (lik == MGP_LIK_GAUSSIAN && !lik_var) return fail(c, MGP_ERR_BAD_ARG, "e_log_p_y: Gaussian likelihood needs lik_var");
     if (N == 0) return MGP_OK;
     CUDA_TRY(c, cudaSetDevice(c->device));
-    c->pre_valid = false;
+    c->pre_valid = false; c->kl_valid = false;
     TRY(check_layer(c, pred));
     const int K = pred->K;
     TRY(ensure(c, c->scratch_rb, (size_t)N * K * 8 * 2));
@@ -602,12 +620,22 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
     {
         HostTimer ht("precompute launches");
         Timed t(c, ST_PRECOMPUTE);
+        // three concurrent chains: the Cholesky chain of each layer (single-CTA, latency-bound kernels: the critical
+        // path) and, on the aux stream, everything that depends on q_mu / q_sqrt only, including the KL terms (they
+        // used to sit on the serial tail of mgp_elbo_finish)
         const Launch ls = fork_side(c);
-        precompute_layer(sp.dev, true, (int*)c->status.p, ln);
-        precompute_layer(sa.dev, true, (int*)c->status.p, ls);
+        const Launch lx = fork_aux(c);
+        precompute_chol(sp.dev, true, (int*)c->status.p, ln);
+        precompute_chol(sa.dev, true, (int*)c->status.p, ls);
+        precompute_lq(sp.dev, true, lx);
+        precompute_lq(sa.dev, true, lx);
+        prior_kl_precomputed(sp.dev, (double*)c->kl.p, lx);
+        prior_kl_precomputed(sa.dev, (double*)c->kl.p + 1, lx);
         join_side(c);
+        join_aux(c);
     }
     c->pre_valid = true;
+    c->kl_valid = true;
     if (N_local == 0) return MGP_OK;   // an empty shard contributes zeros
 
     const int Mp_max = sp.dev.Mp > sa.dev.Mp ? sp.dev.Mp : sa.dev.Mp;
@@ -702,6 +730,7 @@ int mgp_elbo_finish(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, 
         precompute_layer(sa.dev, true, (int*)c->status.p, ls);
         join_side(c);
         c->pre_valid = true;
+        c->kl_valid = false;
     }
     const int K = pred->K;
     const LayerRB rp = layer_rb(RB_HEADER, sp.dev.Mp, sp.dev.Dp, K);
@@ -711,9 +740,9 @@ int mgp_elbo_finish(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, 
     Timed t_finish(c, ST_FINISH);
     const Launch ls = fork_side(c);
     finish_layer(sp.dev, reduce_buf + rp.S, reduce_buf + rp.mraw, reduce_buf + rp.esum, reduce_buf + RB_SUMV_PRED, kl_coef,
-                 pg->Z, pg->q_mu, pg->q_sqrt, pg->variance, pg->lengthscales, kl, ln);
+                 pg->Z, pg->q_mu, pg->q_sqrt, pg->variance, pg->lengthscales, c->kl_valid ? nullptr : kl, ln);
     finish_layer(sa.dev, reduce_buf + ra.S, reduce_buf + ra.mraw, reduce_buf + ra.esum, reduce_buf + RB_SUMV_ASSIGN, kl_coef,
-                 ag->Z, ag->q_mu, ag->q_sqrt, ag->variance, ag->lengthscales, kl + 1, ls);
+                 ag->Z, ag->q_mu, ag->q_sqrt, ag->variance, ag->lengthscales, c->kl_valid ? nullptr : kl + 1, ls);
     join_side(c);
     elbo_finalize_kernel<<<1, 32, 0, c->stream>>>(reduce_buf, kl, cfg->num_data, K, elbo,
                                                   cfg->lik == MGP_LIK_GAUSSIAN ? lik_var_grad : nullptr,
@@ -741,7 +770,7 @@ int mgp_debug_kuu_chol(mgp_ctx* c, const mgp_layer* layer, double* Kuu, double* 
     if (!c) return MGP_ERR_BAD_ARG;
     if (!Kuu || !L || !Linv) return fail(c, MGP_ERR_BAD_ARG, "debug_kuu_chol: NULL output");
     CUDA_TRY(c, cudaSetDevice(c->device));
-    c->pre_valid = false;
+    c->pre_valid = false; c->kl_valid = false;
     TRY(setup_layer(c, c->slot[0], layer, false));
     precompute_layer(c->slot[0].dev, false, (int*)c->status.p, launch_of(c));
     const LayerDev& d = c->slot[0].dev;

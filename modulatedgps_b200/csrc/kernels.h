@@ -17,8 +17,11 @@ struct Launch {
 // ---- precompute.cu : replicated O(M^2 D + M^3) work ------------------------------------------------
 // Kuu, Cholesky, L^-1 and the fragment-major operands.  need_bwd adds Q_k = 2(Lq_k Lq_k^T - I).
 void precompute_layer(const LayerDev& ly, bool need_bwd, int* d_status, const Launch& ln);
+void precompute_chol(const LayerDev& ly, bool need_bwd, int* d_status, const Launch& ln);   // Kuu, L, L^-1 chain
+void precompute_lq(const LayerDev& ly, bool need_bwd, const Launch& ln);                    // q_mu / q_sqrt chain
 // gauss_kl(q_mu, q_sqrt) of a whitened layer (only needs Lq_rm allocated)
 void prior_kl_layer(const LayerDev& ly, double* kl_out, const Launch& ln);
+void prior_kl_precomputed(const LayerDev& ly, double* kl_out, const Launch& ln);
 // dst[i] = sum_s src[s*stride + i], i < n (deterministic order)
 void reduce_partials(double* dst, const double* src, int64_t n, int nparts, int64_t stride, bool accumulate,
                      const Launch& ln);

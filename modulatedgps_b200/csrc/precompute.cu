@@ -310,8 +310,12 @@ __global__ void q_finish_kernel(LayerDev ly) {
     ly.Q_rm[(size_t)i * K * Mp + (size_t)k * Mp + j] = 2.0 * (ly.T1[idx] - ((i == j && i < M) ? 1.0 : 0.0));
 }
 
-void precompute_layer(const LayerDev& ly, bool need_bwd, int* d_status, const Launch& ln) {
-    const int Mp = ly.Mp, K = ly.K;
+// The replicated per-step pre-compute of a layer is two independent chains (api.cu runs them on different streams):
+//   precompute_chol : Z / lengthscales, Kuu, its Cholesky factor, L^-1 and its packed forms — a latency-bound chain of
+//                     single-CTA kernels, the critical path in front of the first streaming kernel;
+//   precompute_lq   : everything that depends on q_mu / q_sqrt only (packed Lq_k^T, Lq_k, q_mu, Q_k = 2 (Lq_k Lq_k^T - I)).
+void precompute_chol(const LayerDev& ly, bool need_bwd, int* d_status, const Launch& ln) {
+    const int Mp = ly.Mp;
     const int64_t mm = (int64_t)Mp * Mp;
     prep_z_kernel<<<1, 1024, 0, ln.stream>>>(ly);
     kuu_kernel<<<(unsigned)((mm + 255) / 256), 256, 0, ln.stream>>>(ly);
@@ -322,7 +326,12 @@ void precompute_layer(const LayerDev& ly, bool need_bwd, int* d_status, const La
     trinv_kernel<<<Mp / 32, 256, 0, ln.stream>>>(ly.L, ly.Dinv, ly.Linv, Mp);
     ln.tick(2);
     pack_fm(ly.W_Linv, Mp, Mp, 0, Mp, ly.Linv, Mp, Mp, Mp, false, 1, 0, 0, ln);
-    pack_fm(ly.W_LinvT, Mp, Mp, 0, Mp, ly.Linv, Mp, Mp, Mp, true, 1, 0, 0, ln);
+    if (need_bwd) pack_fm(ly.W_LinvT, Mp, Mp, 0, Mp, ly.Linv, Mp, Mp, Mp, true, 1, 0, 0, ln);
+}
+
+void precompute_lq(const LayerDev& ly, bool need_bwd, const Launch& ln) {
+    const int Mp = ly.Mp, K = ly.K;
+    const int64_t mm = (int64_t)Mp * Mp;
     lq_clean_kernel<<<(unsigned)((K * mm + 255) / 256), 256, 0, ln.stream>>>(ly);
     ln.tick();
     pack_fm(ly.W_LqT, Mp, Mp, 0, Mp, ly.Lq_rm, Mp, Mp, Mp, true, K, mm, mm, ln);
@@ -334,6 +343,11 @@ void precompute_layer(const LayerDev& ly, bool need_bwd, int* d_status, const La
         pack_fm(ly.W_Lq, Mp, Mp, 0, Mp, ly.Lq_rm, Mp, Mp, Mp, false, K, mm, mm, ln);
         pack_fm(ly.W_m, Mp, KP, 0, KP, ly.q_mu, K, ly.M, K, false, 1, 0, 0, ln);
     }
+}
+
+void precompute_layer(const LayerDev& ly, bool need_bwd, int* d_status, const Launch& ln) {
+    precompute_chol(ly, need_bwd, d_status, ln);
+    precompute_lq(ly, need_bwd, ln);
 }
 
 // --------------------------------------------------------------------------------------------------
@@ -427,7 +441,7 @@ __global__ void gqmu_kernel(LayerDev ly, const double* mraw, double kl_coef, dou
     gqmu[idx] = mraw[(size_t)i * KP + k] + kl_coef * ly.q_mu[idx];
 }
 
-// T2 = tril(T2 + q_mu mraw^T)
+// T2 = tril(sum_k T1[k] + q_mu mraw^T)     (T1[k] = Q_k S_k, one batched GEMM instead of one with a K Mp long k-loop)
 __global__ void t_finish_kernel(LayerDev ly, const double* mraw) {
     const int Mp = ly.Mp, M = ly.M, K = ly.K;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -435,7 +449,7 @@ __global__ void t_finish_kernel(LayerDev ly, const double* mraw) {
     const int i = idx / Mp, j = idx % Mp;
     double v = 0.0;
     if (j <= i) {
-        v = ly.T2[idx];
+        for (int k = 0; k < K; ++k) v += ly.T1[(size_t)k * Mp * Mp + idx];
         if (i < M && j < M)
             for (int k = 0; k < K; ++k) v += ly.q_mu[(size_t)i * K + k] * mraw[(size_t)j * KP + k];
     }
@@ -575,7 +589,7 @@ void prior_kl_layer(const LayerDev& ly, double* kl_out, const Launch& ln) {
 
 void finish_layer(const LayerDev& ly, const double* S_lower, const double* mraw, const double* esum,
                   const double* sumv, double kl_coef, double* gZ, double* gqmu, double* gqsqrt, double* gvar,
-                  double* gls, double* kl_out, const Launch& ln) {
+                  double* gls, double* kl_out, const Launch& ln) {   // kl_out == nullptr: the KL term is already there
     const int Mp = ly.Mp, K = ly.K, M = ly.M;
     const int64_t mm = (int64_t)Mp * Mp;
     const unsigned gmm = (unsigned)((mm + 255) / 256);
@@ -587,7 +601,8 @@ void finish_layer(const LayerDev& ly, const double* S_lower, const double* mraw,
     gqmu_kernel<<<(M * K + 255) / 256, 256, 0, ln.stream>>>(ly, mraw, kl_coef, gqmu);
     ln.tick(2);
     // T = tril( sum_k Q_k S_k + q_mu mraw^T )  ( = Abar A^T )
-    gemm_small(Mp, Mp, K * Mp, 1.0, ly.Q_rm, K * Mp, 0, false, ly.Sfull, Mp, 0, false, 0.0, ly.T2, Mp, 0, 1, ln);
+    // (T1 = S_k Lq_k has been consumed by gqsqrt_kernel above; it now takes the K partial products Q_k S_k)
+    gemm_small(Mp, Mp, Mp, 1.0, ly.Q_rm, K * Mp, Mp, false, ly.Sfull, Mp, mm, false, 0.0, ly.T1, Mp, mm, K, ln);
     t_finish_kernel<<<gmm, 256, 0, ln.stream>>>(ly, mraw);
     // Lbar = -tril(L^-T T)
     gemm_small(Mp, Mp, Mp, 1.0, ly.Linv, Mp, 0, true, ly.T2, Mp, 0, false, 0.0, ly.T3, Mp, 0, 1, ln);
@@ -602,7 +617,10 @@ void finish_layer(const LayerDev& ly, const double* S_lower, const double* mraw,
     kuu_bwd_kernel<<<M, 128, 0, ln.stream>>>(ly, ly.T3, ly.rowout);
     assemble_kernel<<<1, 256, 0, ln.stream>>>(ly, esum, ly.rowout, sumv, gZ, gvar, gls);
     ln.tick(2);
-    kl_launch(ly, kl_out, ln);
+    if (kl_out) kl_launch(ly, kl_out, ln);
 }
+
+// KL term of a layer whose Lq_rm is current (precompute_layer has run)
+void prior_kl_precomputed(const LayerDev& ly, double* kl_out, const Launch& ln) { kl_launch(ly, kl_out, ln); }
 
 }  // namespace mgp

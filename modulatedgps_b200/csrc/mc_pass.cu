@@ -21,6 +21,9 @@ namespace mgp {
 
 constexpr double REPARAM_JITTER = 1e-6;  // config.default_jitter() in reparameterize, MixtureGPs/utils.py:27
 constexpr int MC_THREADS = 128;
+#ifndef MC_MIN_CTAS
+#define MC_MIN_CTAS 4
+#endif
 constexpr double HALF_LOG_2PI = 0.91893853320467274178;
 
 // ---- Philox4x32-10 (throughput mode) --------------------------------------------------------------
@@ -199,7 +202,7 @@ __device__ __forceinline__ void load_noise(const McArgs& a, int64_t i, int s, do
 }
 
 template <int K, int MODEL, int LIK>
-__global__ void __launch_bounds__(MC_THREADS) mc_pass_kernel(McArgs a, double* block_part) {
+__global__ void __launch_bounds__(MC_THREADS, MC_MIN_CTAS) mc_pass_kernel(McArgs a, double* block_part) {
     __shared__ double red[32];
     const int64_t i = (int64_t)blockIdx.x * MC_THREADS + threadIdx.x;
     const bool live = i < a.n;

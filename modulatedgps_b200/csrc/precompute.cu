@@ -198,66 +198,81 @@ __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_kernel(double* L, double
 // --------------------------------------------------------------------------------------------------
 // X = L^-1 by block forward substitution, one CTA per 32-column block of X (X pre-zeroed):
 //   X_ij = V_i (delta_ij I - sum_{j <= p < i} L_ip X_pj),   V_i = (L_ii)^-1 from chol_kernel.
-// The L_ip and X_pj blocks are staged through shared memory, the next pair fetched into registers while the current
-// one is multiplied (the scalar loop over global memory this replaces paid an L2 round trip per 4 columns).
+// The chain over i is serial, so a step has to be short: the block products L_ip X_pj of a step are dealt to the 8
+// warps by p (the k-range is split, every warp forms a full 32 x 32 partial on DMMA from operands fetched in ONE
+// round trip), the partials are summed through shared memory, and V_i R is another 16 DMMAs per warp.
+// (A thread-per-output FMA loop over staged blocks took 4.9 k clocks per 32-deep chunk and 99 us in all: four
+// dependent FP64 FMA chains per thread, ~35 clocks per link.)
 // --------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) trinv_kernel(const double* L, const double* Dinv, double* X, int Mp) {
-    __shared__ double Ls[32][33];
-    __shared__ __align__(16) double Xs[32][36];
-    __shared__ __align__(16) double R[32][36];
-    __shared__ double Vs[32][33];
-    const int jb = blockIdx.x, nblk = Mp / 32, tid = threadIdx.x;
-    const int r = tid >> 3, c4 = (tid & 7) * 4;
+constexpr int TI_WARPS = 8;
+constexpr int TI_SMEM_DOUBLES = TI_WARPS * 1024 + 32 * 36;
+
+__global__ void __launch_bounds__(TI_WARPS * 32, 1) trinv_kernel(const double* L, const double* Dinv, double* X, int Mp) {
+    extern __shared__ __align__(16) double ti_sm[];
+    double* part = ti_sm;                    // [TI_WARPS][16 fragments][32 lanes][2]   C-fragment layout
+    double* R = ti_sm + TI_WARPS * 1024;     // [32][36]
+    const int jb = blockIdx.x, nblk = Mp / 32, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int smi = warp >> 1, sni = (warp & 1) * 2;   // the two output fragments (smi, sni), (smi, sni + 1) of the V_i R product
     for (int ib = jb; ib < nblk; ++ib) {
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        double lreg[4], xreg[4];
-        auto fetch = [&](int pb) {
+        double v[8];   // row block smi of V_i (lower triangular: k4-blocks past the diagonal are zero)
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int idx = tid + 256 * m, rr = idx >> 5, cc = idx & 31;
-                lreg[m] = L[(size_t)(ib * 32 + rr) * Mp + pb * 32 + cc];
-                xreg[m] = X[(size_t)(pb * 32 + rr) * Mp + jb * 32 + cc];
-            }
-        };
-        if (jb < ib) fetch(jb);
-        for (int pb = jb; pb < ib; ++pb) {
+        for (int kk = 0; kk < 8; ++kk)
+            v[kk] = (kk < 2 * (smi + 1)) ? Dinv[((size_t)ib * 32 + smi * 8 + g) * 32 + kk * 4 + t] : 0.0;
+        const int nch = ib - jb;
+        if (warp < nch) {
+            double acc[4][4][2];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                const int idx = tid + 256 * m, rr = idx >> 5, cc = idx & 31;
-                Ls[rr][cc] = lreg[m];
-                Xs[rr][cc] = xreg[m];
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            for (int pb = jb + warp; pb < ib; pb += TI_WARPS) {
+                double a[4][8], b[4][8];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        a[mi][kk] = L[(size_t)(ib * 32 + mi * 8 + g) * Mp + pb * 32 + kk * 4 + t];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        b[ni][kk] = X[(size_t)(pb * 32 + kk * 4 + t) * Mp + jb * 32 + ni * 8 + g];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni], a[mi][kk], b[ni][kk]);
             }
-            __syncthreads();
-            if (pb + 1 < ib) fetch(pb + 1);
-#pragma unroll 8
-            for (int p = 0; p < 32; ++p) {
-                const double l = Ls[r][p];
-                const double2 x01 = *reinterpret_cast<const double2*>(&Xs[p][c4]);
-                const double2 x23 = *reinterpret_cast<const double2*>(&Xs[p][c4 + 2]);
-                acc[0] = fma(l, x01.x, acc[0]);
-                acc[1] = fma(l, x01.y, acc[1]);
-                acc[2] = fma(l, x23.x, acc[2]);
-                acc[3] = fma(l, x23.y, acc[3]);
-            }
-            __syncthreads();
+            double* mine = part + (size_t)warp * 1024 + lane * 2;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni)
+                    *reinterpret_cast<double2*>(mine + (mi * 4 + ni) * 64) = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) R[r][c4 + q] = ((ib == jb && r == c4 + q) ? 1.0 : 0.0) - acc[q];
-        for (int idx = tid; idx < 1024; idx += 256) Vs[idx >> 5][idx & 31] = Dinv[(size_t)ib * 1024 + idx];
         __syncthreads();
-        double o[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int k = 0; k <= r; ++k) {   // V_i is lower triangular
-            const double v = Vs[r][k];
-            const double2 r01 = *reinterpret_cast<const double2*>(&R[k][c4]);
-            const double2 r23 = *reinterpret_cast<const double2*>(&R[k][c4 + 2]);
-            o[0] = fma(v, r01.x, o[0]);
-            o[1] = fma(v, r01.y, o[1]);
-            o[2] = fma(v, r23.x, o[2]);
-            o[3] = fma(v, r23.y, o[3]);
-        }
-        double* xo = X + (size_t)(ib * 32 + r) * Mp + jb * 32 + c4;
+        const int np = nch < TI_WARPS ? nch : TI_WARPS;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) xo[q] = o[q];
+        for (int q = 0; q < 4; ++q) {
+            const int pos = tid + 256 * q, f = pos >> 6, l = (pos >> 1) & 31, e = pos & 1;
+            double s = 0.0;
+            for (int w = 0; w < np; ++w) s += part[(size_t)w * 1024 + pos];
+            const int row = (f >> 2) * 8 + (l >> 2), col = (f & 3) * 8 + 2 * (l & 3) + e;
+            R[row * 36 + col] = ((ib == jb && row == col) ? 1.0 : 0.0) - s;
+        }
+        __syncthreads();
+        double o[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+            if (kk < 2 * (smi + 1)) {
+                dmma(o[0], v[kk], R[(kk * 4 + t) * 36 + sni * 8 + g]);
+                dmma(o[1], v[kk], R[(kk * 4 + t) * 36 + (sni + 1) * 8 + g]);
+            }
+        double* xo = X + (size_t)(ib * 32 + smi * 8 + g) * Mp + jb * 32 + sni * 8 + 2 * t;
+        xo[0] = o[0][0]; xo[1] = o[0][1];
+        xo[8] = o[1][0]; xo[9] = o[1][1];
         __syncthreads();   // the block just written is read (from global memory) by this CTA's later steps
     }
 }
@@ -323,7 +338,8 @@ void precompute_chol(const LayerDev& ly, bool need_bwd, int* d_status, const Lau
     cudaMemcpyAsync(ly.L, ly.Kuu, sizeof(double) * mm, cudaMemcpyDeviceToDevice, ln.stream);
     chol_kernel<<<1, CHOL_THREADS, 0, ln.stream>>>(ly.L, ly.Dinv, Mp, d_status);
     cudaMemsetAsync(ly.Linv, 0, sizeof(double) * mm, ln.stream);
-    trinv_kernel<<<Mp / 32, 256, 0, ln.stream>>>(ly.L, ly.Dinv, ly.Linv, Mp);
+    cudaFuncSetAttribute(trinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TI_SMEM_DOUBLES * sizeof(double)));
+    trinv_kernel<<<Mp / 32, TI_WARPS * 32, TI_SMEM_DOUBLES * sizeof(double), ln.stream>>>(ly.L, ly.Dinv, ly.Linv, Mp);
     ln.tick(2);
     pack_fm(ly.W_Linv, Mp, Mp, 0, Mp, ly.Linv, Mp, Mp, Mp, false, 1, 0, 0, ln);
     if (need_bwd) pack_fm(ly.W_LinvT, Mp, Mp, 0, Mp, ly.Linv, Mp, Mp, Mp, true, 1, 0, 0, ln);

@@ -2,8 +2,11 @@
 // C[b] = alpha * opA(A[b]) * opB(B[b]) + beta * C[b], row-major.
 // These GEMMs are O(M^3), replicated on every rank and LATENCY-bound (a 256^3 product is 3.6 us of DMMA time on the
 // whole chip): the tile is small (32x32, 4 warps of 16x16) so that even one 256 x 256 output spreads over 64 CTAs, and
-// the k-chunks of 32 are double-buffered with 8-byte cp.async (any transpose / stride), so a chunk costs one
-// shared-memory round trip instead of a global one.  The streaming kernels (stream_kernels.cu, syrk.cu) carry the
+// the k-chunks of 32 are double-buffered with cp.async, so a chunk costs one shared-memory round trip instead of a
+// global one.  Aligned, full-tile operands (every call of the replicated pre/post-compute: Mp is a multiple of 32) are
+// staged with 16-byte copies along the contiguous source direction — a transposed operand is stored transposed and its
+// fragments are read the other way round; the general path keeps 8-byte copies with range checks (the LSU retires
+// 8-byte asynchronous copies element by element: 2048 per chunk cost ~2.7 k clocks, a 256^3 product 14 us).  The streaming kernels (stream_kernels.cu, syrk.cu) carry the
 // O(N M^2) work.
 #include "common.cuh"
 #include "kernels.h"
@@ -33,8 +36,29 @@ __global__ void __launch_bounds__(GS_THREADS) gemm_small_kernel(int m, int n, in
 #pragma unroll
         for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    // vector path: 16-byte aligned bases and leading dimensions, no partial tiles
+    const bool vec = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0 && (lda & 1) == 0 &&
+                     (ldb & 1) == 0 && m % GS_BM == 0 && n % GS_BN == 0 && k % GS_BK == 0;
+    const bool aT = vec && transA;   // A chunk stored [k][m]
+    const bool bT = vec && transB;   // B chunk stored [n][k]
     // stage the k-chunk starting at k0 into buffer `buf`; out-of-range elements are written as zeros directly
     auto stage = [&](int k0, int buf) {
+        if (vec) {
+            for (int idx = tid; idx < GS_BM * GS_BK / 2; idx += GS_THREADS) {
+                const int r = idx / (GS_BK / 2), c = (idx % (GS_BK / 2)) * 2;   // smem row r, columns c, c + 1
+                // !transA: row = m, col = k, source A[m][k];   transA: row = k, col = m, source A[k][m]
+                const double* src = transA ? A + (size_t)(k0 + r) * lda + m0 + c : A + (size_t)(m0 + r) * lda + k0 + c;
+                cp_async16(&As[buf][r * GS_AS + c], src);
+            }
+            for (int idx = tid; idx < GS_BK * GS_BN / 2; idx += GS_THREADS) {
+                const int r = idx / (GS_BN / 2), c = (idx % (GS_BN / 2)) * 2;
+                // !transB: row = k, col = n, source B[k][n];   transB: row = n, col = k, source B[n][k]
+                const double* src = transB ? B + (size_t)(n0 + r) * ldb + k0 + c : B + (size_t)(k0 + r) * ldb + n0 + c;
+                cp_async16(&Bs[buf][r * GS_BS + c], src);
+            }
+            cp_async_commit();
+            return;
+        }
         for (int idx = tid; idx < GS_BM * GS_BK; idx += GS_THREADS) {
             int mm, kk;   // thread mapping follows the contiguous source direction
             if (transA) { mm = idx % GS_BM; kk = idx / GS_BM; } else { kk = idx % GS_BK; mm = idx / GS_BK; }
@@ -66,9 +90,11 @@ __global__ void __launch_bounds__(GS_THREADS) gemm_small_kernel(int m, int n, in
         for (int ks = 0; ks < GS_BK / 4; ++ks) {
             double a[2], b[2];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) a[i] = as[(wr + i * 8 + g) * GS_AS + ks * 4 + t];
+            for (int i = 0; i < 2; ++i)
+                a[i] = aT ? as[(ks * 4 + t) * GS_AS + wr + i * 8 + g] : as[(wr + i * 8 + g) * GS_AS + ks * 4 + t];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) b[j] = bs[(ks * 4 + t) * GS_BS + wc + j * 8 + g];
+            for (int j = 0; j < 2; ++j)
+                b[j] = bT ? bs[(wc + j * 8 + g) * GS_BS + ks * 4 + t] : bs[(ks * 4 + t) * GS_BS + wc + j * 8 + g];
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll

@@ -616,6 +616,16 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
     const LayerRB rp = layer_rb(RB_HEADER, sp.dev.Mp, sp.dev.Dp, K);
     const LayerRB ra = layer_rb(rp.end, sa.dev.Mp, sa.dev.Dp, K);
     CUDA_TRY(c, cudaMemsetAsync(reduce_buf, 0, sizeof(double) * ra.end, c->stream));
+    const int maxparts = stream_max_parts(ln);
+    LayerSlot* slots[2] = {&sp, &sa};
+    for (LayerSlot* s : slots) {
+        const size_t Mp = s->dev.Mp, E = 1 + 2 * s->dev.Dp;
+        s->nsplit = syrk_num_splits(s->dev.Mp, K, ln);
+        TRY(ensure(c, s->syrk_part, (size_t)s->nsplit * K * Mp * Mp * 8));
+        TRY(ensure(c, s->mraw_part, (size_t)s->nsplit * Mp * KP * 8));
+        TRY(ensure(c, s->esum_part, (size_t)maxparts * Mp * E * 8));
+        s->esum_nparts = 0;
+    }
 
     {
         HostTimer ht("precompute launches");
@@ -627,6 +637,12 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
         const Launch lx = fork_aux(c);
         precompute_chol(sp.dev, true, (int*)c->status.p, ln);
         precompute_chol(sa.dev, true, (int*)c->status.p, ls);
+        for (LayerSlot* s : slots) {   // the per-CTA partial-sum buffers (76 MB at config #4) are cleared beside the Cholesky chains
+            const size_t Mp = s->dev.Mp, E = 1 + 2 * s->dev.Dp;
+            CUDA_TRY(c, cudaMemsetAsync(s->syrk_part.p, 0, (size_t)s->nsplit * K * Mp * Mp * 8, c->aux));
+            CUDA_TRY(c, cudaMemsetAsync(s->mraw_part.p, 0, (size_t)s->nsplit * Mp * KP * 8, c->aux));
+            CUDA_TRY(c, cudaMemsetAsync(s->esum_part.p, 0, (size_t)maxparts * Mp * E * 8, c->aux));
+        }
         precompute_lq(sp.dev, true, lx);
         precompute_lq(sa.dev, true, lx);
         prior_kl_precomputed(sp.dev, (double*)c->kl.p, lx);
@@ -645,19 +661,6 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
     HostTimer ht_rest("elbo_local after pick_chunk");
     TRY(ensure_chunk(c, sp, ldn, true));
     TRY(ensure_chunk(c, sa, ldn, true));
-    const int maxparts = stream_max_parts(ln);
-    LayerSlot* slots[2] = {&sp, &sa};
-    for (LayerSlot* s : slots) {
-        const size_t Mp = s->dev.Mp, E = 1 + 2 * s->dev.Dp;
-        s->nsplit = syrk_num_splits(s->dev.Mp, K, ln);
-        TRY(ensure(c, s->syrk_part, (size_t)s->nsplit * K * Mp * Mp * 8));
-        TRY(ensure(c, s->mraw_part, (size_t)s->nsplit * Mp * KP * 8));
-        TRY(ensure(c, s->esum_part, (size_t)maxparts * Mp * E * 8));
-        CUDA_TRY(c, cudaMemsetAsync(s->syrk_part.p, 0, (size_t)s->nsplit * K * Mp * Mp * 8, c->stream));
-        CUDA_TRY(c, cudaMemsetAsync(s->mraw_part.p, 0, (size_t)s->nsplit * Mp * KP * 8, c->stream));
-        CUDA_TRY(c, cudaMemsetAsync(s->esum_part.p, 0, (size_t)maxparts * Mp * E * 8, c->stream));
-        s->esum_nparts = 0;
-    }
     const int nblocks_max = mc_num_blocks(ldn);
     TRY(ensure(c, c->mc_part, (size_t)nblocks_max * MC_NPART * 8));
 
@@ -698,14 +701,17 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
     }
     const LayerRB* rbs[2] = {&rp, &ra};
     Timed t_reduce(c, ST_REDUCE);
+    const Launch lside = fork_side(c);   // the two layers' partial sums are independent: one stream each
     for (int i = 0; i < 2; ++i) {
         LayerSlot* s = slots[i];
+        const Launch& lr = i == 0 ? ln : lside;
         const int64_t Mp = s->dev.Mp, E = 1 + 2 * s->dev.Dp;
         reduce_partials(reduce_buf + rbs[i]->S, (const double*)s->syrk_part.p, (int64_t)K * Mp * Mp, s->nsplit,
-                        (int64_t)K * Mp * Mp, false, ln);
-        reduce_partials(reduce_buf + rbs[i]->mraw, (const double*)s->mraw_part.p, Mp * KP, s->nsplit, Mp * KP, false, ln);
-        reduce_partials(reduce_buf + rbs[i]->esum, (const double*)s->esum_part.p, Mp * E, s->esum_nparts, Mp * E, false, ln);
+                        (int64_t)K * Mp * Mp, false, lr);
+        reduce_partials(reduce_buf + rbs[i]->mraw, (const double*)s->mraw_part.p, Mp * KP, s->nsplit, Mp * KP, false, lr);
+        reduce_partials(reduce_buf + rbs[i]->esum, (const double*)s->esum_part.p, Mp * E, s->esum_nparts, Mp * E, false, lr);
     }
+    join_side(c);
     CUDA_TRY(c, cudaGetLastError());
     return MGP_OK;
 }

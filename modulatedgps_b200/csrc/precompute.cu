@@ -531,12 +531,17 @@ __global__ void __launch_bounds__(1024) kl_part_kernel(LayerDev ly, double* part
     double s = 0.0;
     if (k < K) {
         const double* Lq = ly.Lq_rm + (size_t)k * Mp * Mp;
-        for (int i = c; i < M; i += KL_NC)
-            for (int j = threadIdx.x; j <= i; j += blockDim.x) {
+        // flat walk over the M x M square (fixed thread -> element map, so the sum order is fixed): a row-per-iteration
+        // loop kept a quarter of the CTA busy and paid one L2 round trip per row (38 us at M = 256)
+#pragma unroll 4
+        for (int idx = c * blockDim.x + threadIdx.x; idx < M * M; idx += KL_NC * blockDim.x) {
+            const int i = idx / M, j = idx - i * M;
+            if (j <= i) {
                 const double v = Lq[(size_t)i * Mp + j];
                 s += v * v;
                 if (i == j) s -= log(v * v);
             }
+        }
     } else {
         for (int idx = c * blockDim.x + threadIdx.x; idx < M * K; idx += KL_NC * blockDim.x) {
             const double v = ly.q_mu[idx];

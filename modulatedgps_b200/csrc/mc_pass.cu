@@ -38,16 +38,29 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
     }
 }
 
-// one standard normal and one uniform on (0,1) for (global point, sample, component, stream)
-__device__ __forceinline__ void philox_draw(uint64_t seed, int64_t point, int s, int k, int stream, double& z,
-                                            double& u) {
-    uint32_t c[4] = {(uint32_t)point, (uint32_t)((uint64_t)point >> 32), (uint32_t)s, (uint32_t)(k | (stream << 8))};
-    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    const double ua = ((double)c[0] + 0.5) * (1.0 / 4294967296.0);
-    const double ub = ((double)c[1] + 0.5) * (1.0 / 4294967296.0);
-    z = sqrt(-2.0 * log(ua)) * cospi(2.0 * ub);
-    const uint64_t r53 = (((uint64_t)c[2] << 32) | c[3]) >> 11;
-    u = ((double)r53 + 0.5) * (1.0 / 9007199254740992.0);
+// K standard normals and K uniforms on (0,1) for (global point, sample, stream): one Philox block per component
+// (counter = point, sample, component | stream << 8) gives the component's 53-bit uniform; the normals come in
+// Box-Muller PAIRS from the even component's block — radius and angle once, cosine branch for component k, sine branch
+// for k + 1 (a log, a sqrt and a cospi per component would cost half as much FP64-pipe time again).
+template <int K>
+__device__ __forceinline__ void philox_draw_all(uint64_t seed, int64_t point, int s, int stream, double (&z)[K],
+                                                double (&u)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        uint32_t c[4] = {(uint32_t)point, (uint32_t)((uint64_t)point >> 32), (uint32_t)s, (uint32_t)(k | (stream << 8))};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const uint64_t r53 = (((uint64_t)c[2] << 32) | c[3]) >> 11;
+        u[k] = ((double)r53 + 0.5) * (1.0 / 9007199254740992.0);
+        if ((k & 1) == 0) {
+            const double ua = ((double)c[0] + 0.5) * (1.0 / 4294967296.0);
+            const double ub = ((double)c[1] + 0.5) * (1.0 / 4294967296.0);
+            const double r = sqrt(-2.0 * log(ua));
+            double sn, cs;
+            sincospi(2.0 * ub, &sn, &cs);
+            z[k] = r * cs;
+            if (k + 1 < K) z[k + 1] = r * sn;
+        }
+    }
 }
 
 // ---- RobustMax Gauss-Hermite quadrature (gpflow MultiClass) ----------------------------
@@ -196,8 +209,7 @@ __device__ __forceinline__ void load_noise(const McArgs& a, int64_t i, int s, do
         }
     } else {
         const int64_t point = a.point_offset + a.chunk_offset + i;
-#pragma unroll
-        for (int k = 0; k < K; ++k) philox_draw(a.seed, point, s, k, 0, z[k], u[k]);
+        philox_draw_all<K>(a.seed, point, s, 0, z, u);
     }
 }
 
@@ -468,11 +480,12 @@ __global__ void predict_samples_k(SampleArgs a) {
             z[k] = a.z[((size_t)s * a.n + i) * K + k];
             u[k] = a.u[((size_t)s * a.n + i) * K + k];
             zp[k] = a.z_pred[((size_t)s * a.n + i) * K + k];
-        } else {
-            double dummy;
-            philox_draw(a.seed, a.point_offset + i, s, k, 0, z[k], u[k]);
-            philox_draw(a.seed, a.point_offset + i, s, k, 1, zp[k], dummy);
         }
+    }
+    if (a.z == nullptr) {
+        double dummy[K];
+        philox_draw_all<K>(a.seed, a.point_offset + i, s, 0, z, u);
+        philox_draw_all<K>(a.seed, a.point_offset + i, s, 1, zp, dummy);
     }
     sample_weights<K>(mu_a, sd_a, z, u, 1.0 / a.temperature, W);
     double mu[K], v[K], my[K], vy[K];
@@ -530,10 +543,9 @@ __global__ void w_sample_k(SampleArgs a, double* W_out) {
         if (a.z != nullptr) {
             z[k] = a.z[((size_t)s * a.n + i) * K + k];
             u[k] = a.u[((size_t)s * a.n + i) * K + k];
-        } else {
-            philox_draw(a.seed, a.point_offset + i, s, k, 0, z[k], u[k]);
         }
     }
+    if (a.z == nullptr) philox_draw_all<K>(a.seed, a.point_offset + i, s, 0, z, u);
     sample_weights<K>(mu_a, sd_a, z, u, 1.0 / a.temperature, W);
 #pragma unroll
     for (int k = 0; k < K; ++k) W_out[idx * K + k] = W[k];

@@ -93,6 +93,18 @@ def test_bijectors_roundtrip_and_chain_rule_on_cpu_tensors():
     assert torch.equal(ft.grad_to_unconstrained(g, v), vr.grad)
 
 
+def test_constrained_shapes_need_no_kernel():
+    """Parameter.shape (used once per parameter and step by the gradient plumbing) comes from the bijector's
+    forward_shape, not from evaluating the bijector."""
+    from modulatedgps_b200.parameter import FillTriangular, Identity, Softplus
+    assert Softplus().forward_shape((1, 4)) == (1, 4) and Identity().forward_shape((7, 3)) == (7, 3)
+    ft = FillTriangular()
+    for m in (1, 2, 5, 25, 256):
+        n = m * (m + 1) // 2
+        assert ft.forward_shape((4, n)) == (4, m, m)
+        assert tuple(ft.forward(torch.zeros(4, n, dtype=torch.float64)).shape) == (4, m, m)
+
+
 def test_gauss_hermite_header_matches_numpy():
     src = open(os.path.join(ROOT, "modulatedgps_b200", "csrc", "gh20.h")).read()
     nums = [float(t) for t in re.findall(r"-?\d+\.\d+(?:e-?\d+)?", src.split("GH20_X[20]")[1])]

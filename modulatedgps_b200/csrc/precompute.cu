@@ -37,7 +37,12 @@ __global__ void prep_z_kernel(LayerDev ly) {
             s += v * v;
         }
         ly.zs2[i] = s;
-        ly.zh[i] = log(ly.variance[0]) - 0.5 * s;
+        const double zh = log(ly.variance[0]) - 0.5 * s;
+        ly.zh[i] = zh;
+        if (D + 2 <= Dp) {   // kuf_fold (stream_kernels.cu): the exponent's row term rides in the padding columns of Zs_fm
+            ly.Zs_fm[wf_index(i, D, Dp)] = i < M ? zh : 0.0;
+            ly.Zs_fm[wf_index(i, D + 1, Dp)] = i < M ? 1.0 : 0.0;
+        }
     }
 }
 

@@ -215,6 +215,12 @@ struct WPair {
     }
 };
 
+// When the input dimension leaves two padding columns in the k4-blocks of the zs.xs contraction (D + 2 <= Dp: D = 1, 2,
+// 5, 6, ...), the exponent's row term (log variance - |zs|^2/2) and column term (-|xs|^2/2) ride in them —
+// Zs_fm[i][D] = row term, Zs_fm[i][D+1] = 1 (prep_z_kernel), Xs[n][D] = 1, Xs[n][D+1] = column term — and the DMMA
+// returns the whole exponent: two FP64 additions per Kuf element less on the pipe the kernel is bound by.
+__host__ __device__ inline bool kuf_fold(int D, int Dp) { return D + 2 <= Dp; }
+
 // Xs[n][d] = X[n0+n][d] / lengthscale_d (0 outside the chunk / padding); xs2[n] = -|Xs_n|^2 / 2 (column term of the
 // Kuf exponent).  One warp.
 template <int NT>
@@ -228,10 +234,15 @@ __device__ __forceinline__ void stage_x_warp(const LayerDev& ly, const ChunkBuff
         Xs[n * XSTR + d] = v;
     }
     __syncwarp();
+    const bool fold = kuf_fold(D, Dp);
     for (int n = lane; n < NT; n += 32) {
         double s = 0.0;
-        for (int d = 0; d < Dp; ++d) s += Xs[n * XSTR + d] * Xs[n * XSTR + d];
+        for (int d = 0; d < D; ++d) s += Xs[n * XSTR + d] * Xs[n * XSTR + d];
         xs2[n] = -0.5 * s;
+        if (fold) {   // the two free padding columns of the contraction carry the row and column terms of the exponent
+            Xs[n * XSTR + D] = 1.0;
+            Xs[n * XSTR + D + 1] = -0.5 * s;
+        }
     }
     __syncwarp();
 }
@@ -255,8 +266,15 @@ __device__ __forceinline__ void gen_kuf_block(const LayerDev& ly, int rb8, const
         for (int nf = 0; nf < NF; ++nf) dmma(kv[nf], a, Xs[(nf * 8 + g) * XSTR + kd * 4 + t]);
     }
     const int i = rb8 * 8 + g;
-    const double zh = __ldg(ly.zh + i);
     const bool live = i < ly.M;
+    if (kuf_fold(ly.D, Dp)) {   // (warp-uniform) the contraction already holds the whole exponent
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) kv[nf][e] = live ? exp_tab(kv[nf][e], etab) : 0.0;
+        return;
+    }
+    const double zh = __ldg(ly.zh + i);
 #pragma unroll
     for (int nf = 0; nf < NF; ++nf)
 #pragma unroll

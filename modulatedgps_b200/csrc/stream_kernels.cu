@@ -293,9 +293,9 @@ constexpr int SK_BAR_DOUBLES = 8;   // room for 2 x NBUF mbarriers (NBUF <= 2) +
 
 // ==================================================================================================
 // cond_fwd_a :  A tile = L^-1 * Kuf tile
-// Two CTAs per SM (16 warps): every warp first generates rows of the Kuf tile (exp on the FP64 pipe), then
-// multiplies.  The generation phase is scalar FP64 work that shares the pipe with DMMA, so it wants MANY warps to
-// overlap with the other CTA's DMMA phase — a dedicated generator-warp ring starves behind the consumers' DMMAs
+// As many CTAs per SM as fit (three at config #4: 24 warps): every warp first generates rows of the Kuf tile (exp on
+// the FP64 pipe), then multiplies.  The generation phase is scalar FP64 work that shares the pipe with DMMA, so it wants MANY warps to
+// overlap with the other CTAs' DMMA phases — a dedicated generator-warp ring starves behind the consumers' DMMAs
 // (measured: 9.1 ms vs 6.2 ms for this form at config #4).
 // ==================================================================================================
 template <int NT>

@@ -31,7 +31,7 @@
 namespace mgp {
 
 // exp(x) from a 64-entry table of 2^(j/64) and a degree-5 polynomial on |r| <= ln2/128: 10 FP64 instructions instead
-// of libdevice's 16-18, at most ~1 ulp from it (tools/gen_exp_tab.py).  It matters out of proportion to its pipe time:
+// of libdevice's 16-18, at most 1.03 ulp from expl (tools/exp_tab_check.c, tests/test_host_logic.py).  It matters out of proportion to its pipe time:
 // in the two-CTA kernels a scalar FP64 instruction waits behind the other CTA's 16-clock DMMAs (~30 clocks each,
 // measured), so the Kuf generation phase is as long as its FP64 instruction count.  `tab` is the shared-memory copy.
 __device__ const double d_exp_tab64[64] = {EXP_TAB64_VALUES};

@@ -4,6 +4,7 @@ maps match the TFP conventions, and the bench workload generator is deterministi
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -103,6 +104,23 @@ def test_constrained_shapes_need_no_kernel():
         n = m * (m + 1) // 2
         assert ft.forward_shape((4, n)) == (4, m, m)
         assert tuple(ft.forward(torch.zeros(4, n, dtype=torch.float64)).shape) == (4, m, m)
+
+
+def test_exp_tab_is_accurate_to_an_ulp(tmp_path):
+    """The table exponential of the Kuf kernels (csrc/stream_kernels.cu::exp_tab, csrc/exp_tab.h), restated in C with
+    the same constants and operation order, stays within 1.1 ulp of expl() over [-700, 700] (2 M samples here;
+    tools/exp_tab_check.c runs 20 M by default)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "exp_tab_check")
+    subprocess.run(["gcc", "-O2", "-o", exe, os.path.join(ROOT, "tools", "exp_tab_check.c"), "-lm"], check=True)
+    r = subprocess.run([exe, "2000000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # the header is what tools/gen_exp_tab.py generates
+    gen = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_exp_tab.py")], capture_output=True, text=True, check=True)
+    assert gen.stdout == open(os.path.join(ROOT, "modulatedgps_b200", "csrc", "exp_tab.h")).read()
 
 
 def test_gauss_hermite_header_matches_numpy():

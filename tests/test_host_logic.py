@@ -41,6 +41,33 @@ def test_ctypes_struct_layout_matches_header():
     assert _lib.MgpElboCfg.temperature.offset == 16 and _lib.MgpElboCfg.n_global.offset == 32
 
 
+def test_header_is_plain_c_and_ctypes_mirrors_it_field_by_field(tmp_path):
+    """include/mgp.h compiles as C (no C++ / torch types at the boundary) and every field of every ctypes mirror sits at
+    the offset the C compiler gives it."""
+    import shutil
+    import subprocess
+    from modulatedgps_b200 import _lib
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    mirrors = {"mgp_layer": _lib.MgpLayer, "mgp_layer_grad": _lib.MgpLayerGrad, "mgp_noise": _lib.MgpNoise,
+               "mgp_elbo_cfg": _lib.MgpElboCfg, "mgp_adam_slot": _lib.MgpAdamSlot}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "mgp.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", exe, str(src)], check=True)
+    out = dict(l.split() for l in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in mirrors.items():
+        assert int(out[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback(built_lib):
     import modulatedgps_b200 as mg

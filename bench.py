@@ -38,62 +38,80 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-N_TOTAL = 1 << 20
-D, M, K, S = 2, 256, 4, 16
 FP64_PEAK_TFLOPS = 37.0      # measured DMMA.8x8x4 issue-rate peak on this pool's B200 (profiles/r01_fp64_peak_microbench.txt)
 DGEMM_TFLOPS = 35.4          # cuBLAS DGEMM 8192^3 on the same box (profiles/r01_dgemm_peak.json)
 
 
-def flops_per_point(m=M, k=K, d=D):
-    """algorithmic flops per point, two layers, forward + backward."""
-    return 6 * (k + 1) * m * m + 12 * m * (d + 2 * k + 1)
+class Cfg:
+    """The benchmarked configuration: BASELINE.json configs[3] (#4, the one `metric` is quoted on; default) or
+    configs[4] (#5, the Kuf-streaming / FP64 DMMA stress shape) — sizes from modulatedgps_b200.workloads."""
+
+    def __init__(self, which, points=None):
+        from modulatedgps_b200.workloads import CONFIG4, CONFIG5
+        c = {4: CONFIG4, 5: CONFIG5}[which]
+        self.which = which
+        self.N, self.D, self.M, self.K, self.S = (points or c["N"]), c["D"], c["M"], c["K"], c["S"]
+        self.N_full = c["N"]
+
+    def flops_per_point(self):
+        """algorithmic flops per point, two layers, forward + backward."""
+        return 6 * (self.K + 1) * self.M * self.M + 12 * self.M * (self.D + 2 * self.K + 1)
+
+    def executed_algorithm_flops_per_point(self):
+        """The same count without the M^2 / point / layer of the L-bar reduction, which the S_k reformulation
+         removes from the algorithm altogether: (4 + 6K) M^2 + the O(M) terms."""
+        return (4 + 6 * self.K) * self.M * self.M + 12 * self.M * (self.D + 2 * self.K + 1)
+
+    def kernel_flops_per_point(self):
+        """(algorithmic, executed) flops per point, both layers, of each streaming kernel (SURVEY.md §8d / Appendix B,
+        per layer: cond_fwd_a M^2, cond_fwd_b K M^2, syrk K M^2, cond_bwd_a K M^2, cond_bwd_b M^2).  Executed =
+        algorithmic x the padding of the triangular blocking: 16-row blocks ((nb+1)/nb), with the two all-zero fragments
+        of every diagonal 16 x 16 block skipped ((2nb+1)/2nb) in cond_fwd_b / cond_bwd_a / cond_bwd_b; SYRK computes
+        64 x 64 tile pairs (36 of 64 fragments on diagonal pairs) for M(M+1)/2 / 64 algorithmic 8 x 8 fragments."""
+        M, K = self.M, self.K
+        Mp = (M + 31) // 32 * 32
+        nb = Mp // 16
+        nb64 = (Mp + 63) // 64
+        syrk_pad = (64 * nb64 * (nb64 - 1) // 2 + 36 * nb64) / (M * (M + 1) / 2 / 64)
+        unit = {"cond_fwd_a": 1, "cond_fwd_b": K, "syrk": K, "cond_bwd_a": K, "cond_bwd_b": 1}
+        alg = {k: 2 * u * M * M for k, u in unit.items()}
+        pad = {"cond_fwd_a": (nb + 1) / nb * (Mp / M) ** 2, "cond_fwd_b": (2 * nb + 1) / (2 * nb) * (Mp / M) ** 2,
+               "syrk": syrk_pad, "cond_bwd_a": (2 * nb + 1) / (2 * nb) * (Mp / M) ** 2,
+               "cond_bwd_b": (2 * nb + 1) / (2 * nb) * (Mp / M) ** 2}
+        return alg, {k: alg[k] * pad[k] for k in alg}
 
 
-def make_workload(n_points, seed=0, m=M, k=K, d=D):
-    """Config #4 synthetic inputs and parameters."""
-    rng = np.random.default_rng(seed)
-    side = int(round(math.sqrt(m)))
-    X = rng.uniform(0.0, float(side), (n_points, d))
-    comp = rng.integers(0, k, n_points)
-    r1 = np.random.default_rng(1)
-    om, ph = r1.uniform(0.5, 1.5, (k, d)), r1.uniform(0, 2 * np.pi, k)
-    Y = (np.sin((X * om[comp]).sum(1) + ph[comp]) + 1.5 * comp + 0.1 * rng.standard_normal(n_points))[:, None]
-    r2 = np.random.default_rng(2)
-    g = np.linspace(0.5, side - 0.5, side)
-    grid = np.stack(np.meshgrid(g, g, indexing="ij"), -1).reshape(-1, d)
-
-    def layer(var, ls):
-        Z = grid + r2.uniform(-0.2, 0.2, grid.shape)
-        q = np.stack([np.eye(m) + 0.05 * np.tril(r2.standard_normal((m, m))) for _ in range(k)])
-        idx = np.arange(m)
-        q[:, idx, idx] = np.abs(q[:, idx, idx]) + 0.05
-        return {"variance": np.float64(var), "lengthscales": np.asarray(ls, dtype=np.float64), "Z": Z,
-                "q_mu": 0.3 * r2.standard_normal((m, k)), "q_sqrt": q}
-
-    case = {"model": "SMGP", "lik": "gaussian", "K": k, "S": S, "num_data": float(N_TOTAL),
-            "pred": layer(1.0, [1.0] * d), "assign": layer(0.5, [1.5] * d), "lik_var": 0.1 + 0.05 * np.arange(k),
-            "assign_lik_var": None}
+def make_workload(cfg, lo, hi):
+    """(case, X[lo:hi], Y[lo:hi]) of the configuration's synthetic data set."""
+    from modulatedgps_b200 import workloads as W
+    if cfg.which == 4:
+        case, X, Y = W.config4_workload(cfg.N, seed=0, num_data=cfg.N)
+        return case, X[lo:hi], Y[lo:hi]
+    case = W.config5_parameters(num_data=cfg.N)
+    X, Y = W.config5_points(lo, hi)
     return case, X, Y
 
 
 # ----------------------------------------------------------------------------------------------------
 # CPU arm: the oracle restatement on the host cores (reported baseline, and `--impl reference`)
 # ----------------------------------------------------------------------------------------------------
-def cpu_points_per_s(chunk=4096, reps=3, warmup=1):
+def cpu_points_per_s(cfg, chunk=4096, reps=3, warmup=1, literal=False):
+    """ELBO fwd+bwd of oracle/svgp_mixture.py on `chunk` of the configuration's points with every host core.
+    literal=True: the S-tiled formulation the reference's TF graph executes (S-fold the conditional work)."""
     import torch
     from oracle import svgp_mixture as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    case, X, Y = make_workload(chunk, seed=0)
+    case, X, Y = make_workload(cfg, 0, chunk)
     rng = np.random.default_rng(3)
-    z = rng.standard_normal((S, chunk, K))
-    u = rng.uniform(np.finfo(np.float64).tiny, 1.0, (S, chunk, K))
+    z = rng.standard_normal((cfg.S, chunk, cfg.K))
+    u = rng.uniform(np.finfo(np.float64).tiny, 1.0, (cfg.S, chunk, cfg.K))
     pred, assign = O.layer_from_numpy(case["pred"]), O.layer_from_numpy(case["assign"])
     times = []
     for it in range(warmup + reps):
         t0 = time.perf_counter()
         O.elbo_and_grads("SMGP", "gaussian", pred, assign, O.as_t(case["lik_var"]), None, X, Y, z, u, case["num_data"],
-                         n_total=N_TOTAL)
+                         n_total=cfg.N, literal=literal)
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -104,15 +122,17 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    chunk = 8192
-    value, cores, times = cpu_points_per_s(chunk=chunk, reps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
-    sample = (f"{chunk} of the {N_TOTAL} config-#4 points per step, ELBO fwd+bwd (torch autograd) of oracle/svgp_mixture.py, "
-              f"explicit noise, {cores} torch threads")
+    cfg = Cfg(args.config, args.points)
+    chunk = 8192 if cfg.which == 4 else 2048
+    warm = max(0, args.warmup)
+    value, cores, times = cpu_points_per_s(cfg, chunk=chunk, reps=max(1, args.steps), warmup=warm)
+    sample = (f"{chunk} of the {cfg.N} config-#{cfg.which} points per step, ELBO fwd+bwd (torch autograd) of "
+              f"oracle/svgp_mixture.py (de-duplicated over S), explicit noise, {cores} torch threads")
     line = {"impl": "reference", "metric": "elbo_fwd_bwd_points_per_s", "value": value, "unit": "points/s",
-            "n_gpus": args.gpus, "steps": len(times), "warmup": max(1, min(args.warmup, 2)),
+            "n_gpus": args.gpus, "steps": len(times), "warmup": warm,
             "ms_per_step": 1e3 * statistics.median(times), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus),
+            "config": workload_config(cfg, args.gpus),
             "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample,
                              "note": "CPU restatement of the TF2/GPflow path; TensorFlow/GPflow are not installable in this image"},
             "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -120,13 +140,13 @@ def run_reference_arm(args):
     return 0
 
 
-def workload_config(n_gpus):
-    return {"workload": "BASELINE config #4: synthetic N=2^20 (total), D=2, M=256, K=4, S=16, SMGP + GaussianModified, "
-                        "ELBO fwd+bwd step, Philox noise on device",
-            "N": N_TOTAL, "D": D, "M": M, "K": K, "S": S, "points_per_gpu": N_TOTAL // n_gpus,
+def workload_config(cfg, n_gpus):
+    return {"workload": f"BASELINE config #{cfg.which}: synthetic N={cfg.N} (total), D={cfg.D}, M={cfg.M}, K={cfg.K}, "
+                        f"S={cfg.S}, SMGP + GaussianModified, ELBO fwd+bwd step, Philox noise on device",
+            "N": cfg.N, "D": cfg.D, "M": cfg.M, "K": cfg.K, "S": cfg.S, "points_per_gpu": cfg.N // n_gpus,
             "sharding": f"dp{n_gpus}: contiguous row shards, parameters replicated, one all-reduce of the flat reduce buffer",
             "l2": "no explicit flush: each step streams the materialised A (2 layers x M x N/gpus x 8 B = "
-                  f"{2 * M * (N_TOTAL // n_gpus) * 8 / 1e9:.1f} GB) through HBM, far beyond the 126 MB L2"}
+                  f"{2 * cfg.M * (cfg.N // n_gpus) * 8 / 1e9:.1f} GB) through HBM, far beyond the 126 MB L2"}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -187,7 +207,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--points", type=int, default=N_TOTAL, help="total points (default: the config-#4 size)")
+    ap.add_argument("--config", type=int, default=4, choices=[4, 5],
+                    help="BASELINE.json configs[3] (#4: N=2^20, D=2, M=256, K=4, S=16; the headline metric, default) or "
+                         "configs[4] (#5: N=2^24, D=8, M=1024, K=8, S=32; meant for --gpus 8)")
+    ap.add_argument("--points", type=int, default=None, help="total points (default: the configuration's own N)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -212,19 +235,18 @@ def main():
     if args.gpus != world:
         if rank == 0:
             print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
-    n_total = args.points
-    n_local = n_total // world
-    n_total = n_local * world
+    cfg = Cfg(args.config, args.points)
+    n_local = cfg.N // world
+    n_total = cfg.N = n_local * world
 
     import modulatedgps_b200 as mg  # noqa: F401
     from modulatedgps_b200 import _lib
-    from tests.helpers_gpu import build_model
+    from modulatedgps_b200.workloads import model_from_case as build_model
 
-    case, X, Y = make_workload(n_total, seed=0)
-    case["num_data"] = float(n_total)
-    sl = slice(rank * n_local, (rank + 1) * n_local)
-    Xh = torch.as_tensor(X[sl]).contiguous().pin_memory()
-    Yh = torch.as_tensor(Y[sl]).contiguous().pin_memory()
+    case, X, Y = make_workload(cfg, rank * n_local, (rank + 1) * n_local)
+    Xh = torch.as_tensor(X).contiguous().pin_memory()
+    Yh = torch.as_tensor(Y).contiguous().pin_memory()
+    del X, Y
     Xd, Yd = Xh.to(dev), Yh.to(dev)
     model = build_model(case)
     model.seed = 3
@@ -321,25 +343,21 @@ def main():
         # reduction, which this design folds into the S_k algebra); x2 layers)
         # (the survey's F_pt also counts an M^2 L-bar reduction per layer that the S_k formulation removes altogether:
         #  it is part of step_roofline's flops_per_point, not of any kernel's algorithmic work)
-        alg = {"cond_fwd_a": 2 * M * M, "cond_fwd_b": 2 * K * M * M, "syrk": 2 * K * M * M, "cond_bwd_a": 2 * K * M * M,
-               "cond_bwd_b": 2 * M * M}
-        # executed = algorithmic x the padding of the triangular blocking (16-row blocks: 17/16; SYRK: 528 computed
-        # 8x8 fragments for 514 algorithmic ones)
-        # (cond_fwd_b / cond_bwd_a / cond_bwd_b also skip the two all-zero fragments of each diagonal 16 x 16 block: 33/32)
-        executed = {"cond_fwd_a": 2 * M * M * 17 / 16, "cond_fwd_b": 2 * K * M * M * 33 / 32, "syrk": 2 * K * M * M * 528 / 514,
-                    "cond_bwd_a": 2 * K * M * M * 33 / 32, "cond_bwd_b": 2 * M * M * 33 / 32}
+        alg, executed = cfg.kernel_flops_per_point()
         dom = max(alg, key=lambda k: per_stage.get(k, 0.0))
         dom_ms = per_stage[dom]
         achieved = alg[dom] * n_local / (dom_ms * 1e-3) / 1e12
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of that kernel from the committed `ncu --set full`
         # capture of this command at 1 GPU (profiles/r01_kernel_traffic.json); scaled by the shard size
         traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")))
-            if dom in tj["per_launch_dram_bytes"]:
-                traffic = tj["per_launch_dram_bytes"][dom] * n_local / tj["points_per_launch"]
-        except (OSError, KeyError, ValueError):
-            traffic = None
+        for tname in ("r02_kernel_traffic.json", "r01_kernel_traffic.json"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
+                if cfg.which == 4 and dom in tj["per_launch_dram_bytes"]:
+                    traffic = tj["per_launch_dram_bytes"][dom] * n_local / tj["points_per_launch"]
+                    break
+            except (OSError, KeyError, ValueError):
+                continue
         roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                     "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
                     "launches_per_step": 2, "alg_flops_per_launch": alg[dom] * n_local / 2,
@@ -349,25 +367,43 @@ def main():
                                    "(profiles/r01_fp64_peak_microbench.txt); MEASURED_PEAKS.json has no FP64 entry; "
                                    f"cuBLAS DGEMM on the same box: {DGEMM_TFLOPS} TFLOP/s",
                     "kernel_ms_per_step": dom_ms, "kernel_share_of_step": dom_ms / ms_per_step}
-        step_roof_ms = flops_per_point() * n_local / (FP64_PEAK_TFLOPS * 1e12) * 1e3
+        step_roof_ms = cfg.flops_per_point() * n_local / (FP64_PEAK_TFLOPS * 1e12) * 1e3
+        exec_roof_ms = cfg.executed_algorithm_flops_per_point() * n_local / (FP64_PEAK_TFLOPS * 1e12) * 1e3
         line = {"metric": "elbo_fwd_bwd_points_per_s", "value": value, "unit": "points/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": workload_config(world), "clocks": clocks,
+                "config": workload_config(cfg, world), "clocks": clocks,
                 "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
                         "host_wall_ms_per_step": 1e3 * t_host / args.steps,
                         "h2d_bytes_per_step": int(Xh.numel() * 8 + Yh.numel() * 8) * world, "d2h_bytes_per_step": 8 * world,
                         "api": "modulatedgps_b200.SMGP._training_loss((X_host, Y_host)) + loss.backward() + loss.item()"},
                 "gpu_launches": int(launches), "roofline": roofline,
-                "step_roofline": {"flops_per_point": flops_per_point(), "roof_ms_per_step": step_roof_ms,
-                                  "frac_of_fp64_peak": step_roof_ms / ms_per_step, "peak_tflops": FP64_PEAK_TFLOPS},
+                "step_roofline": {"flops_per_point": cfg.flops_per_point(), "roof_ms_per_step": step_roof_ms,
+                                  "frac_of_fp64_peak": step_roof_ms / ms_per_step, "peak_tflops": FP64_PEAK_TFLOPS,
+                                  "e2e_frac_of_fp64_peak": step_roof_ms / e2e_ms,
+                                  "executed_algorithm": {
+                                      "flops_per_point": cfg.executed_algorithm_flops_per_point(),
+                                      "roof_ms_per_step": exec_roof_ms, "frac_of_fp64_peak": exec_roof_ms / ms_per_step,
+                                      "note": "SURVEY's F_pt counts an M^2/point/layer L-bar reduction that the S_k "
+                                              "reformulation removes; this is the count of the algorithm that runs"}},
                 "stages_ms_per_step": per_stage, "loss": final_loss}
         if not args.no_cpu_baseline and world == 1:
-            v, cores, times = cpu_points_per_s(chunk=4096, reps=3, warmup=1)
+            chunk = 4096 if cfg.which == 4 else 1024
+            v, cores, times = cpu_points_per_s(cfg, chunk=chunk, reps=3, warmup=1)
             line["cpu_baseline"] = {"value": v, "unit": "points/s", "cores": cores, "kind": "port",
-                                    "sample": f"4096 of the {N_TOTAL} config-#4 points, 3 timed repetitions after 1 warm-up, "
-                                              "oracle/svgp_mixture.py ELBO fwd+bwd (torch CPU autograd, explicit noise)",
+                                    "sample": f"{chunk} of the {cfg.N} config-#{cfg.which} points, 3 timed repetitions after 1 "
+                                              "warm-up, oracle/svgp_mixture.py ELBO fwd+bwd (torch CPU autograd, explicit "
+                                              "noise), conditionals de-duplicated over S",
                                     "note": "CPU restatement of the TF2/GPflow path; TF/GPflow are not installable here"}
+            if cfg.which == 4:
+                # what the reference's TF graph literally executes: the conditionals on the S tiled copies of X, at the
+                # demos' batch size
+                vl, _, tl = cpu_points_per_s(cfg, chunk=500, reps=3, warmup=1, literal=True)
+                line["cpu_baseline"]["literal"] = {
+                    "value": vl, "unit": "points/s", "cores": cores, "kind": "port",
+                    "sample": "500 of the config-#4 points (the demos' batch size), 3 timed repetitions after 1 warm-up, the "
+                              "same oracle with the S = 16 tiled copies of X evaluated as the reference's graph does "
+                              "(LTA [S, K, M, N] materialised)"}
         else:
             line["cpu_baseline"] = None
         sys.stdout.flush()

@@ -28,6 +28,14 @@ extern "C" {
 #define MGP_ERR_CUDA 2
 #define MGP_ERR_NOT_PD 3   /* Cholesky of Kuu hit a non-positive pivot (TF: InvalidArgumentError) */
 #define MGP_ERR_NOMEM 4
+#define MGP_ERR_STALE_PRECOMPUTE 5   /* parameter values changed in place between mgp_elbo_local and mgp_elbo_finish */
+
+/* gpflow RobustMax.prob_is_largest squashes every Gaussian CDF into (s, 1 - s) before the product over classes:
+ * cdfs = cdfs * (1 - 2 s) + s with the literal s = 1e-4 (gpflow/likelihoods/multiclass.py, 1.x through 2.x; the
+ * attribute RobustMax._squash = 1e-6 is set in __init__ and never read).  oracle/svgp_mixture.py and oracle/shim
+ * carry the same named constant; tests/test_host_logic.py checks the three agree.  DESIGN.md section 3 records the
+ * evidence for 1e-4 over 1e-6 (both were replayed against the reference's published config-#2 trajectory). */
+#define MGP_ROBUSTMAX_CDF_SQUASH 1e-4
 
 #define MGP_MAX_K 8        /* latent GPs (components) per layer */
 #define MGP_MAX_D 32       /* input dimensions */
@@ -95,6 +103,8 @@ int mgp_timing_enable(mgp_ctx* ctx, int on);
 int mgp_timing_read(mgp_ctx* ctx, double* ms, int64_t* calls, int reset);
 int mgp_num_stages(void);
 const char* mgp_stage_name(int i);
+/* Override MGP_ROBUSTMAX_CDF_SQUASH for this context (0 <= s < 0.5) — for the A/B replay of config #2 only. */
+int mgp_set_robustmax_squash(mgp_ctx* ctx, double squash);
 /* cap for the per-call point chunk (0 = automatic: whole shard if the materialised A fits the budget) */
 int mgp_set_chunk_points(mgp_ctx* ctx, int64_t max_points);
 
@@ -132,6 +142,25 @@ int mgp_w_sample(mgp_ctx* ctx, const mgp_layer* assign, const double* X, int64_t
 int mgp_e_log_p_y(mgp_ctx* ctx, const mgp_layer* pred, int32_t lik, const double* lik_var, const double* X,
                   const double* Y, int64_t N, int32_t S, const double* W, double* out);
 
+/* The likelihood methods the reference exposes as stand-alone calls; Fmu / Fvar are [S, N, K] (row r = s N + n reads
+ * Y[n]: the reference tiles Y over the sample axis, MixtureGPs/broadcasting_lik.py:22-37), Y [N] float64 (class index
+ * for MULTICLASS).
+ *   mgp_lik_variational_expectations  BroadcastingLikelihood.variational_expectations (broadcasting_lik.py:39-42):
+ *        GAUSSIAN -> out [S, N, K], GaussianModified._variational_expectations, NOT reduced over k (likelihoods.py:39-41);
+ *        MULTICLASS -> out [S, N] (the reference's [S, N, 1]), gpflow MultiClass._variational_expectations.
+ *   mgp_lik_predict_mean_and_var      BroadcastingLikelihood.predict_mean_and_var (broadcasting_lik.py:44-46):
+ *        GaussianModified._predict_mean_and_var (likelihoods.py:31-32) / MultiClass._predict_mean_and_var; rows = S N.
+ *   mgp_lik_log_prob                  GaussianModified._scalar_log_prob (likelihoods.py:21-22) -> [S, N, K].
+ *   mgp_lik_predict_log_density       GaussianModified._predict_log_density (likelihoods.py:34-35) -> [S, N]. */
+int mgp_lik_variational_expectations(mgp_ctx* ctx, int32_t lik, const double* lik_var, const double* Fmu,
+                                     const double* Fvar, const double* Y, int64_t S, int64_t N, int32_t K, double* out);
+int mgp_lik_predict_mean_and_var(mgp_ctx* ctx, int32_t lik, const double* lik_var, const double* Fmu,
+                                 const double* Fvar, int64_t rows, int32_t K, double* mean, double* var);
+int mgp_lik_log_prob(mgp_ctx* ctx, const double* lik_var, const double* F, const double* Y, int64_t S, int64_t N,
+                     int32_t K, double* out);
+int mgp_lik_predict_log_density(mgp_ctx* ctx, const double* lik_var, const double* Fmu, const double* Fvar,
+                                const double* Y, int64_t S, int64_t N, int32_t K, double* out);
+
 /* Size (in doubles) of the flat reduction buffer of mgp_elbo_local for these layers. */
 int64_t mgp_reduce_buffer_len(const mgp_layer* pred, const mgp_layer* assign);
 
@@ -147,7 +176,11 @@ int mgp_elbo_local(mgp_ctx* ctx, const mgp_elbo_cfg* cfg, const mgp_layer* pred,
 
 /* Phase 2 (replicated): from the (all-reduced) buffer, the KL terms (models.py:79), the Cholesky and
  * kernel backward, and the final gradients w.r.t. constrained values.  elbo [1]; lik_var_grad [K] and
- * assign_lik_var_grad [K] may be NULL when the corresponding likelihood has no variance. */
+ * assign_lik_var_grad [K] may be NULL when the corresponding likelihood has no variance.
+ * The factorisations mgp_elbo_local formed are reused only when `pred` / `assign` are the same layers (dimensions
+ * and parameter pointers); otherwise they are formed again here, so two models may be interleaved on one context.
+ * Parameter VALUES must not change between the two calls: a fingerprint of them is compared on the device and a
+ * mismatch sets elbo = NaN and makes the next mgp_check_status return MGP_ERR_STALE_PRECOMPUTE. */
 int mgp_elbo_finish(mgp_ctx* ctx, const mgp_elbo_cfg* cfg, const mgp_layer* pred, const mgp_layer* assign,
                     const double* lik_var, const double* assign_lik_var, const double* reduce_buf,
                     double* elbo, mgp_layer_grad* pred_grad, mgp_layer_grad* assign_grad,
@@ -177,9 +210,11 @@ typedef struct {
 
 /* One fused Adam update of every trainable variable — replaces tf.optimizers.Adam(lr).minimize(training_loss,
  * model.trainable_variables) of utils/training_utils.py:6-10, TF 2.10 Keras defaults beta1 .9, beta2 .999, eps 1e-7.
- * grad_scale = -1 turns ELBO gradients into gradients of the training loss (models.py:81-83).  step >= 1. */
+ * grad_scale = -1 turns ELBO gradients into gradients of the training loss (models.py:81-83).  step >= 1.
+ * guard: NULL, or a device scalar (the step's ELBO): when it is not finite the whole update is skipped on the device,
+ * without a host synchronisation — a failed Cholesky (NaN ELBO and gradients) never reaches theta, m or v. */
 int mgp_adam_step(void* cuda_stream, const mgp_adam_slot* slots, int32_t nslots, double grad_scale, double lr,
-                  double beta1, double beta2, double eps, int64_t step);
+                  double beta1, double beta2, double eps, int64_t step, const double* guard);
 
 /* Minibatch gather: Xb[r] = X[idx[r]], Yb[r] = Y[idx[r]] — the device half of
  * tf.data.Dataset.from_tensor_slices((X, Y)).shuffle(N).batch(B).repeat() (demos/demo_tf2.py:53-56). */
@@ -200,6 +235,13 @@ int mgp_kmeans_iterate(void* cuda_stream, const double* X, int64_t N, int32_t D,
 /* Stage-level entry points (used by the parity tests to localise a failure; same kernels as above).
  * L, Linv: [M, M] row-major lower-triangular outputs for one layer. */
 int mgp_debug_kuu_chol(mgp_ctx* ctx, const mgp_layer* layer, double* Kuu, double* L, double* Linv);
+/* The throughput-mode noise generator, exposed for known-answer and distribution tests.
+ * mgp_debug_philox: ctr_key uint32 [n][6] = {counter[4], key[2]} -> out uint32 [n][4] = Philox4x32-10 (Random123 KAT).
+ * mgp_debug_noise:  the z (standard normal) and u (uniform) draws [S, N, K] the fused MC pass would use for noise->seed /
+ *                   noise->point_offset; stream 0 = W_dist draws (models.py:57,73), 1 = predict_samples' second z (:98). */
+int mgp_debug_philox(mgp_ctx* ctx, const uint32_t* ctr_key, int32_t n, uint32_t* out);
+int mgp_debug_noise(mgp_ctx* ctx, const mgp_noise* noise, int64_t N, int32_t S, int32_t K, int32_t stream, double* z,
+                    double* u);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmgp.so")
 
-MGP_OK, MGP_ERR_BAD_ARG, MGP_ERR_CUDA, MGP_ERR_NOT_PD, MGP_ERR_NOMEM = 0, 1, 2, 3, 4
+MGP_OK, MGP_ERR_BAD_ARG, MGP_ERR_CUDA, MGP_ERR_NOT_PD, MGP_ERR_NOMEM, MGP_ERR_STALE_PRECOMPUTE = 0, 1, 2, 3, 4, 5
+ROBUSTMAX_CDF_SQUASH = 1e-4      # MGP_ROBUSTMAX_CDF_SQUASH of include/mgp.h (tests/test_host_logic.py keeps them equal)
 MODEL_SMGP, MODEL_SMGP_MODIFIED = 0, 1
 LIK_GAUSSIAN, LIK_MULTICLASS = 0, 1
 MAX_K, MAX_D = 8, 32
@@ -60,6 +61,10 @@ class NotPositiveDefiniteError(MgpError):
     """Cholesky of Kuu failed (the reference surfaces this as a TF InvalidArgumentError)."""
 
 
+class StalePrecomputeError(MgpError):
+    """Parameter values were changed in place between mgp_elbo_local and mgp_elbo_finish."""
+
+
 _lib = None
 
 # every exported symbol of include/mgp.h: (restype, argtypes)
@@ -97,9 +102,21 @@ _PROTOTYPES = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(MgpNoise),
                                    C.c_void_p, C.POINTER(MgpLayerGrad), C.POINTER(MgpLayerGrad), C.c_void_p,
                                    C.c_void_p]),
+    "mgp_lik_variational_expectations": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
+    "mgp_lik_predict_mean_and_var": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                               C.c_int32, C.c_void_p, C.c_void_p]),
+    "mgp_lik_log_prob": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
+                                   C.c_void_p]),
+    "mgp_lik_predict_log_density": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                              C.c_int64, C.c_int32, C.c_void_p]),
+    "mgp_debug_philox": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mgp_debug_noise": (C.c_int, [C.c_void_p, C.POINTER(MgpNoise), C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_void_p, C.c_void_p]),
     "mgp_debug_kuu_chol": (C.c_int, [C.c_void_p, C.POINTER(MgpLayer), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mgp_adam_step": (C.c_int, [C.c_void_p, C.POINTER(MgpAdamSlot), C.c_int32, C.c_double, C.c_double, C.c_double,
-                                C.c_double, C.c_double, C.c_int64]),
+                                C.c_double, C.c_double, C.c_int64, C.c_void_p]),
+    "mgp_set_robustmax_squash": (C.c_int, [C.c_void_p, C.c_double]),
     "mgp_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                   C.c_void_p]),
     "mgp_fill_triangular": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]),
@@ -131,6 +148,7 @@ def load_library():
 
 
 _contexts: Dict[Tuple[int, int], "Context"] = {}
+MAX_CONTEXTS_PER_DEVICE = 2
 
 
 class Context:
@@ -153,6 +171,8 @@ class Context:
         msg = (self.lib.mgp_last_error(self.handle) or b"").decode()
         if rc == MGP_ERR_NOT_PD:
             raise NotPositiveDefiniteError(rc, msg)
+        if rc == MGP_ERR_STALE_PRECOMPUTE:
+            raise StalePrecomputeError(rc, msg)
         raise MgpError(rc, msg)
 
     def check_status(self):
@@ -172,6 +192,9 @@ class Context:
         calls = (C.c_int64 * n)()
         self.check(self.lib.mgp_timing_read(self.handle, ms, calls, 1 if reset else 0))
         return {self.lib.mgp_stage_name(i).decode(): (float(ms[i]), int(calls[i])) for i in range(n)}
+
+    def set_robustmax_squash(self, squash: float):
+        self.check(self.lib.mgp_set_robustmax_squash(self.handle, float(squash)))
 
     def set_chunk_points(self, n: int):
         self.check(self.lib.mgp_set_chunk_points(self.handle, int(n)))
@@ -197,11 +220,16 @@ def get_context(device: torch.device | int | None = None) -> Context:
         dev = int(device)
     stream_ptr = int(torch.cuda.current_stream(dev).cuda_stream)
     key = (dev, stream_ptr)
-    ctx = _contexts.get(key)
+    ctx = _contexts.pop(key, None)
     if ctx is None:
+        # a context owns a workspace of up to 40 % of HBM: keep at most MAX_CONTEXTS_PER_DEVICE alive per device and
+        # drop the least recently used one (a recycled stream handle then gets a fresh context, never a stale one)
+        mine = [k for k in _contexts if k[0] == dev]
+        while len(mine) >= MAX_CONTEXTS_PER_DEVICE:
+            _contexts.pop(mine.pop(0))
         with torch.cuda.device(dev):
             ctx = Context(dev, stream_ptr)
-        _contexts[key] = ctx
+    _contexts[key] = ctx                     # (re)inserted last: dict order is the LRU order
     return ctx
 
 

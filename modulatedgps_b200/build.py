@@ -20,10 +20,20 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
+nvcc_invocations = 0                     # how often this process ran nvcc (the cache test reads it)
+
+
+def _count():
+    global nvcc_invocations
+    nvcc_invocations += 1
+
+
 def _digest() -> str:
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for name in sorted(os.listdir(root)):
+            if name.startswith(".") or not name.endswith((".cu", ".cuh", ".h")):
+                continue                 # sources only: never the stamp itself, editor droppings or objects
             with open(os.path.join(root, name), "rb") as f:
                 h.update(name.encode() + b"\0" + f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -31,7 +41,7 @@ def _digest() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    stamp = os.path.join(HERE, "csrc", ".build_stamp")
+    stamp = os.path.join(HERE, "build", ".build_stamp")
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB
@@ -45,6 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
+        _count()
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
         if verbose:

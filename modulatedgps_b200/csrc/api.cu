@@ -92,6 +92,10 @@ struct mgp_ctx {
     LayerSlot slot[2];
     Buf mc_part, scratch_rb, kl, status;
     bool pre_valid = false;
+    // what the precompute held in slot[0..1] was formed from: finish() re-forms it when it is handed other layers
+    mgp_layer pre_layer[2] = {};
+    double rm_squash = MGP_ROBUSTMAX_CDF_SQUASH;
+    Buf fprint;              // uint64 [4]: parameter fingerprints at mgp_elbo_local [0..1] and at mgp_elbo_finish [2..3]
     bool kl_valid = false;   // the KL terms in `kl` belong to the current precompute (formed by mgp_elbo_local)
     bool pick_valid = false;
     int64_t pick_key[5] = {0, 0, 0, 0, 0};
@@ -100,6 +104,20 @@ struct mgp_ctx {
 };
 
 namespace {
+
+// every entry point runs on the context's device and puts the caller's current device back on return
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) err = cudaSetDevice(device); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_CTX_DEVICE(c)                     \
+    DeviceGuard dev_guard__((c)->device);    \
+    CUDA_TRY(c, dev_guard__.err)
 
 int fail(mgp_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
@@ -312,9 +330,48 @@ int64_t pick_chunk_uncached(mgp_ctx* c, int64_t N, int Mp_max, int nlayers, int 
     return N < cap ? N : cap;
 }
 
+// Order-sensitive 64-bit fingerprint of a layer's parameter VALUES (Z, q_mu, variance, lengthscales and the diagonal
+// of every q_sqrt_k — an optimiser step moves all of them): mgp_elbo_finish compares the one taken when
+// mgp_elbo_local formed L, L^-1, Lq ... with the values it is handed, so parameters changed in place between the two
+// calls are reported (MGP_ERR_STALE_PRECOMPUTE through mgp_check_status, ELBO = NaN) instead of silently mixing two
+// parameter states in the Cholesky backward.  One CTA per layer.
+struct FingerprintArgs { mgp_layer l[2]; };
+__global__ void __launch_bounds__(256) fingerprint_kernel(FingerprintArgs a, unsigned long long* out) {
+    __shared__ unsigned long long red[8];
+    const mgp_layer& l = a.l[blockIdx.x];
+    const int64_t nz = (int64_t)l.M * l.D, nm = (int64_t)l.M * l.K, nd = (int64_t)l.K * l.M;
+    const int64_t total = nz + nm + 1 + l.n_lengthscales + nd;
+    unsigned long long h = 0;
+    for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+        int64_t j = i;
+        double v;
+        if (j < nz) v = l.Z[j];
+        else if ((j -= nz) < nm) v = l.q_mu[j];
+        else if ((j -= nm) < 1) v = l.variance[0];
+        else if ((j -= 1) < l.n_lengthscales) v = l.lengthscales[j];
+        else { j -= l.n_lengthscales; const int64_t k = j / l.M, r = j % l.M; v = l.q_sqrt[(k * l.M + r) * l.M + r]; }
+        h += (unsigned long long)__double_as_longlong(v) * (unsigned long long)(2 * i + 1);
+    }
+    for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = h;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        out[blockIdx.x] = t;
+    }
+}
+
 __global__ void elbo_finalize_kernel(const double* rb, const double* kl, double num_data, int K, double* elbo,
-                                     double* glik, double* galik) {
-    if (threadIdx.x == 0) elbo[0] = rb[RB_DATA] - (kl[0] + kl[1]) / num_data;
+                                     double* glik, double* galik, const unsigned long long* fprint, int* status) {
+    const bool stale = fprint != nullptr && (fprint[0] != fprint[2] || fprint[1] != fprint[3]);
+    // a Cholesky pivot was not positive since the last mgp_check_status: whatever the factorisation left behind, the
+    // caller must see a non-finite ELBO (mgp_adam_step's guard keys on it; TF raises InvalidArgumentError here)
+    const bool not_pd = (*status & 1) != 0;
+    if (threadIdx.x == 0) {
+        elbo[0] = (stale || not_pd) ? nan("") : rb[RB_DATA] - (kl[0] + kl[1]) / num_data;
+        if (stale) atomicOr(status, 2);
+    }
     if (threadIdx.x < K) {
         if (glik) glik[threadIdx.x] = rb[RB_LIKVAR + threadIdx.x];
         if (galik) galik[threadIdx.x] = rb[RB_ALIKVAR + threadIdx.x];
@@ -369,7 +426,8 @@ int mgp_ctx_create(int device, void* cuda_stream, mgp_ctx** out) {
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) return MGP_ERR_CUDA;   // no CPU fallback
-    if (cudaSetDevice(device) != cudaSuccess) return MGP_ERR_CUDA;
+    DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return MGP_ERR_CUDA;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MGP_ERR_CUDA;
     mgp_ctx* c = new mgp_ctx();
@@ -386,7 +444,7 @@ int mgp_ctx_create(int device, void* cuda_stream, mgp_ctx** out) {
         delete c;
         return MGP_ERR_CUDA;
     }
-    if (ensure(c, c->kl, 64) != MGP_OK || ensure(c, c->status, 64, true) != MGP_OK) {
+    if (ensure(c, c->kl, 64) != MGP_OK || ensure(c, c->status, 64, true) != MGP_OK || ensure(c, c->fprint, 64, true) != MGP_OK) {
         delete c;
         return MGP_ERR_NOMEM;
     }
@@ -396,7 +454,7 @@ int mgp_ctx_create(int device, void* cuda_stream, mgp_ctx** out) {
 
 void mgp_ctx_destroy(mgp_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     cudaStreamSynchronize(c->stream);
     auto rel = [](Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; };
     for (auto& s : c->slot) {
@@ -406,7 +464,7 @@ void mgp_ctx_destroy(mgp_ctx* c) {
                       &s.syrk_plan};
         for (Buf* b : all) rel(*b);
     }
-    rel(c->mc_part); rel(c->scratch_rb); rel(c->kl); rel(c->status);
+    rel(c->mc_part); rel(c->scratch_rb); rel(c->kl); rel(c->status); rel(c->fprint);
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
     if (c->aux) { cudaStreamSynchronize(c->aux); cudaStreamDestroy(c->aux); }
     if (c->ev_fork_aux) cudaEventDestroy(c->ev_fork_aux);
@@ -426,8 +484,15 @@ int mgp_set_chunk_points(mgp_ctx* c, int64_t max_points) {
     return MGP_OK;
 }
 
+int mgp_set_robustmax_squash(mgp_ctx* c, double squash) {
+    if (!c || !(squash >= 0.0) || !(squash < 0.5)) return c ? fail(c, MGP_ERR_BAD_ARG, "robustmax squash must be in [0, 0.5)") : MGP_ERR_BAD_ARG;
+    c->rm_squash = squash;
+    return MGP_OK;
+}
+
 int mgp_timing_enable(mgp_ctx* c, int on) {
     if (!c) return MGP_ERR_BAD_ARG;
+    ON_CTX_DEVICE(c);
     c->timer.collect(c->stream);
     c->timer.on = on != 0;
     return MGP_OK;
@@ -435,6 +500,7 @@ int mgp_timing_enable(mgp_ctx* c, int on) {
 
 int mgp_timing_read(mgp_ctx* c, double* ms, int64_t* calls, int reset) {
     if (!c || !ms || !calls) return MGP_ERR_BAD_ARG;
+    ON_CTX_DEVICE(c);
     c->timer.collect(c->stream);
     for (int i = 0; i < ST_COUNT; ++i) { ms[i] = c->timer.ms[i]; calls[i] = c->timer.calls[i]; }
     if (reset) for (int i = 0; i < ST_COUNT; ++i) { c->timer.ms[i] = 0.0; c->timer.calls[i] = 0; }
@@ -447,21 +513,23 @@ const char* mgp_stage_name(int i) { return (i >= 0 && i < ST_COUNT) ? kStageName
 
 int mgp_check_status(mgp_ctx* c) {
     if (!c) return MGP_ERR_BAD_ARG;
+    ON_CTX_DEVICE(c);
     int h = 0;
     CUDA_TRY(c, cudaMemcpyAsync(&h, c->status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaGetLastError());
-    if (h & 1) {
-        cudaMemsetAsync(c->status.p, 0, sizeof(int), c->stream);
-        return fail(c, MGP_ERR_NOT_PD, "Cholesky of Kuu + jitter I failed: matrix is not positive definite");
-    }
+    if (h) cudaMemsetAsync(c->status.p, 0, sizeof(int), c->stream);
+    if (h & 1) return fail(c, MGP_ERR_NOT_PD, "Cholesky of Kuu + jitter I failed: matrix is not positive definite");
+    if (h & 2)
+        return fail(c, MGP_ERR_STALE_PRECOMPUTE, "mgp_elbo_finish: parameter values changed after mgp_elbo_local factorised "
+                                                 "them (ELBO set to NaN; call mgp_elbo_local again)");
     return MGP_OK;
 }
 
 int mgp_svgp_predict_f(mgp_ctx* c, const mgp_layer* layer, const double* X, int64_t N, double* fmean, double* fvar) {
     if (!c) return MGP_ERR_BAD_ARG;
     if (N < 0 || (N > 0 && (!X || !fmean || !fvar))) return fail(c, MGP_ERR_BAD_ARG, "predict_f: bad arguments");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    ON_CTX_DEVICE(c);
     c->pre_valid = false; c->kl_valid = false;
     TRY(setup_layer(c, c->slot[0], layer, false));
     if (N == 0) return MGP_OK;
@@ -474,7 +542,7 @@ int mgp_svgp_predict_f(mgp_ctx* c, const mgp_layer* layer, const double* X, int6
 int mgp_prior_kl(mgp_ctx* c, const mgp_layer* layer, double* kl) {
     if (!c) return MGP_ERR_BAD_ARG;
     if (!kl) return fail(c, MGP_ERR_BAD_ARG, "prior_kl: NULL output");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    ON_CTX_DEVICE(c);
     c->pre_valid = false; c->kl_valid = false;
     TRY(setup_layer(c, c->slot[0], layer, false));
     prior_kl_layer(c->slot[0].dev, kl, launch_of(c));
@@ -486,9 +554,10 @@ int mgp_predict_y(mgp_ctx* c, const mgp_layer* pred, int32_t lik, const double* 
                   double* mean, double* var) {
     if (!c) return MGP_ERR_BAD_ARG;
     if (lik == MGP_LIK_GAUSSIAN && !lik_var) return fail(c, MGP_ERR_BAD_ARG, "predict_y: Gaussian likelihood needs lik_var");
+    ON_CTX_DEVICE(c);
     TRY(mgp_svgp_predict_f(c, pred, X, N, mean, var));
     if (N == 0) return MGP_OK;
-    predict_y_kernel(mean, var, N, pred->K, lik, lik_var, mean, var, launch_of(c));
+    predict_y_kernel(mean, var, N, pred->K, lik, lik_var, c->rm_squash, mean, var, launch_of(c));
     CUDA_TRY(c, cudaGetLastError());
     return MGP_OK;
 }
@@ -497,6 +566,7 @@ int mgp_predict_assign(mgp_ctx* c, const mgp_layer* assign, const double* X, int
     if (!c) return MGP_ERR_BAD_ARG;
     if (N > 0 && (!probs || !argmax)) return fail(c, MGP_ERR_BAD_ARG, "predict_assign: NULL output");
     if (N == 0) return MGP_OK;
+    ON_CTX_DEVICE(c);
     TRY(ensure(c, c->scratch_rb, (size_t)N * assign->K * 8));
     TRY(mgp_svgp_predict_f(c, assign, X, N, probs, (double*)c->scratch_rb.p));
     predict_assign_kernel(probs, N, assign->K, probs, argmax, launch_of(c));
@@ -513,7 +583,7 @@ int mgp_predict_samples(mgp_ctx* c, const mgp_layer* pred, const mgp_layer* assi
         return fail(c, MGP_ERR_BAD_ARG, "predict_samples: z, u and z_pred must be given together");
     if (lik == MGP_LIK_GAUSSIAN && !lik_var) return fail(c, MGP_ERR_BAD_ARG, "predict_samples: needs lik_var");
     if (N == 0) return MGP_OK;
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    ON_CTX_DEVICE(c);
     c->pre_valid = false; c->kl_valid = false;
     TRY(check_layer(c, pred));
     TRY(check_layer(c, assign));
@@ -530,7 +600,7 @@ int mgp_predict_samples(mgp_ctx* c, const mgp_layer* pred, const mgp_layer* assi
     precompute_layer(c->slot[1].dev, false, (int*)c->status.p, ln);
     TRY(run_predict_f(c, c->slot[1], X, N, fm_a, fv_a));
     SampleArgs a;
-    a.S = S; a.K = K; a.lik = lik; a.temperature = temperature; a.n = N;
+    a.S = S; a.K = K; a.lik = lik; a.temperature = temperature; a.squash = c->rm_squash; a.n = N;
     a.fmean_p = fm_p; a.fvar_p = fv_p; a.fmean_a = fm_a; a.fvar_a = fv_a; a.lik_var = lik_var;
     a.z = noise->z; a.u = noise->u; a.z_pred = z_pred; a.seed = noise->seed; a.point_offset = noise->point_offset;
     a.samples_y = samples_y; a.samples_f = samples_f;
@@ -546,7 +616,7 @@ int mgp_w_sample(mgp_ctx* c, const mgp_layer* assign, const double* X, int64_t N
         return fail(c, MGP_ERR_BAD_ARG, "w_sample: bad arguments");
     if ((noise->z == nullptr) != (noise->u == nullptr)) return fail(c, MGP_ERR_BAD_ARG, "w_sample: z and u must be given together");
     if (N == 0) return MGP_OK;
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    ON_CTX_DEVICE(c);
     c->pre_valid = false; c->kl_valid = false;
     TRY(check_layer(c, assign));
     const int K = assign->K;
@@ -559,7 +629,7 @@ int mgp_w_sample(mgp_ctx* c, const mgp_layer* assign, const double* X, int64_t N
     TRY(run_predict_f(c, c->slot[1], X, N, fm, fv));
     SampleArgs a;
     memset(&a, 0, sizeof(a));
-    a.S = S; a.K = K; a.lik = 0; a.temperature = temperature; a.n = N;
+    a.S = S; a.K = K; a.lik = 0; a.temperature = temperature; a.squash = c->rm_squash; a.n = N;
     a.fmean_a = fm; a.fvar_a = fv;
     a.z = noise->z; a.u = noise->u; a.seed = noise->seed; a.point_offset = noise->point_offset;
     w_sample_kernel(a, W, ln);
@@ -574,7 +644,7 @@ int mgp_e_log_p_y(mgp_ctx* c, const mgp_layer* pred, int32_t lik, const double* 
     if (lik != MGP_LIK_GAUSSIAN && lik != MGP_LIK_MULTICLASS) return fail(c, MGP_ERR_BAD_ARG, "e_log_p_y: lik");
     if (lik == MGP_LIK_GAUSSIAN && !lik_var) return fail(c, MGP_ERR_BAD_ARG, "e_log_p_y: Gaussian likelihood needs lik_var");
     if (N == 0) return MGP_OK;
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    ON_CTX_DEVICE(c);
     c->pre_valid = false; c->kl_valid = false;
     TRY(check_layer(c, pred));
     const int K = pred->K;
@@ -585,7 +655,71 @@ int mgp_e_log_p_y(mgp_ctx* c, const mgp_layer* pred, int32_t lik, const double* 
     TRY(setup_layer(c, c->slot[0], pred, false));
     precompute_layer(c->slot[0].dev, false, (int*)c->status.p, ln);
     TRY(run_predict_f(c, c->slot[0], X, N, fm, fv));
-    e_log_p_y_kernel(fm, fv, Y, lik_var, lik, W, S, N, K, out, ln);
+    e_log_p_y_kernel(fm, fv, Y, lik_var, lik, c->rm_squash, W, S, N, K, out, ln);
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
+static int lik_call(mgp_ctx* c, int mode, int32_t lik, const double* lik_var, const double* Fmu, const double* Fvar,
+                    const double* Y, int64_t S, int64_t N, int32_t K, double* out, const char* what) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    if (S < 0 || N < 0 || K < 1 || K > MGP_MAX_K) return fail(c, MGP_ERR_BAD_ARG, std::string(what) + ": bad sizes");
+    if (lik != MGP_LIK_GAUSSIAN && lik != MGP_LIK_MULTICLASS) return fail(c, MGP_ERR_BAD_ARG, std::string(what) + ": lik");
+    if (lik == MGP_LIK_GAUSSIAN && !lik_var) return fail(c, MGP_ERR_BAD_ARG, std::string(what) + ": Gaussian likelihood needs lik_var");
+    if (lik == MGP_LIK_MULTICLASS && (mode != 0 || K < 2)) return fail(c, MGP_ERR_BAD_ARG, std::string(what) + ": not defined for MultiClass");
+    if (S * N == 0) return MGP_OK;
+    if (!Fmu || !Y || !out || (mode != 1 && !Fvar)) return fail(c, MGP_ERR_BAD_ARG, std::string(what) + ": NULL argument");
+    ON_CTX_DEVICE(c);
+    lik_eval_kernel(mode, lik, lik_var, c->rm_squash, Fmu, Fvar, Y, S * N, N, K, out, launch_of(c));
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
+int mgp_lik_variational_expectations(mgp_ctx* c, int32_t lik, const double* lik_var, const double* Fmu, const double* Fvar,
+                                     const double* Y, int64_t S, int64_t N, int32_t K, double* out) {
+    return lik_call(c, 0, lik, lik_var, Fmu, Fvar, Y, S, N, K, out, "lik_variational_expectations");
+}
+
+int mgp_lik_log_prob(mgp_ctx* c, const double* lik_var, const double* F, const double* Y, int64_t S, int64_t N, int32_t K,
+                     double* out) {
+    return lik_call(c, 1, MGP_LIK_GAUSSIAN, lik_var, F, nullptr, Y, S, N, K, out, "lik_log_prob");
+}
+
+int mgp_lik_predict_log_density(mgp_ctx* c, const double* lik_var, const double* Fmu, const double* Fvar, const double* Y,
+                                int64_t S, int64_t N, int32_t K, double* out) {
+    return lik_call(c, 2, MGP_LIK_GAUSSIAN, lik_var, Fmu, Fvar, Y, S, N, K, out, "lik_predict_log_density");
+}
+
+int mgp_lik_predict_mean_and_var(mgp_ctx* c, int32_t lik, const double* lik_var, const double* Fmu, const double* Fvar,
+                                 int64_t rows, int32_t K, double* mean, double* var) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    if (rows < 0 || K < 1 || K > MGP_MAX_K) return fail(c, MGP_ERR_BAD_ARG, "lik_predict_mean_and_var: bad sizes");
+    if (lik != MGP_LIK_GAUSSIAN && lik != MGP_LIK_MULTICLASS) return fail(c, MGP_ERR_BAD_ARG, "lik_predict_mean_and_var: lik");
+    if (lik == MGP_LIK_GAUSSIAN && !lik_var) return fail(c, MGP_ERR_BAD_ARG, "lik_predict_mean_and_var: needs lik_var");
+    if (lik == MGP_LIK_MULTICLASS && K < 2) return fail(c, MGP_ERR_BAD_ARG, "lik_predict_mean_and_var: MultiClass needs K >= 2");
+    if (rows == 0) return MGP_OK;
+    if (!Fmu || !Fvar || !mean || !var) return fail(c, MGP_ERR_BAD_ARG, "lik_predict_mean_and_var: NULL argument");
+    ON_CTX_DEVICE(c);
+    predict_y_kernel(Fmu, Fvar, rows, K, lik, lik_var, c->rm_squash, mean, var, launch_of(c));
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
+int mgp_debug_philox(mgp_ctx* c, const uint32_t* ctr_key, int32_t n, uint32_t* out) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    if (n < 0 || (n > 0 && (!ctr_key || !out))) return fail(c, MGP_ERR_BAD_ARG, "debug_philox: bad arguments");
+    ON_CTX_DEVICE(c);
+    philox_kat_kernel(ctr_key, n, out, launch_of(c));
+    CUDA_TRY(c, cudaGetLastError());
+    return MGP_OK;
+}
+
+int mgp_debug_noise(mgp_ctx* c, const mgp_noise* noise, int64_t N, int32_t S, int32_t K, int32_t stream, double* z, double* u) {
+    if (!c) return MGP_ERR_BAD_ARG;
+    if (!noise || N < 0 || S < 1 || K < 1 || K > MGP_MAX_K || stream < 0 || stream > 255 || (N > 0 && (!z || !u)))
+        return fail(c, MGP_ERR_BAD_ARG, "debug_noise: bad arguments");
+    ON_CTX_DEVICE(c);
+    philox_draws_kernel(noise->seed, noise->point_offset, N, S, K, stream, z, u, launch_of(c));
     CUDA_TRY(c, cudaGetLastError());
     return MGP_OK;
 }
@@ -607,7 +741,7 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
     if (N_local < 0 || !noise || !reduce_buf || (N_local > 0 && (!X || !Y)))
         return fail(c, MGP_ERR_BAD_ARG, "elbo_local: bad arguments");
     if ((noise->z == nullptr) != (noise->u == nullptr)) return fail(c, MGP_ERR_BAD_ARG, "noise: z and u must be given together");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    ON_CTX_DEVICE(c);
     const Launch ln = launch_of(c);
     LayerSlot &sp = c->slot[0], &sa = c->slot[1];
     TRY(setup_layer(c, sp, pred, true));
@@ -647,11 +781,19 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
         precompute_lq(sa.dev, true, lx);
         prior_kl_precomputed(sp.dev, (double*)c->kl.p, lx);
         prior_kl_precomputed(sa.dev, (double*)c->kl.p + 1, lx);
+        {
+            FingerprintArgs fa;
+            fa.l[0] = *pred; fa.l[1] = *assign;
+            fingerprint_kernel<<<2, 256, 0, c->aux>>>(fa, (unsigned long long*)c->fprint.p);
+            c->launches += 1;
+        }
         join_side(c);
         join_aux(c);
     }
     c->pre_valid = true;
     c->kl_valid = true;
+    c->pre_layer[0] = *pred;
+    c->pre_layer[1] = *assign;
     if (N_local == 0) return MGP_OK;   // an empty shard contributes zeros
 
     const int Mp_max = sp.dev.Mp > sa.dev.Mp ? sp.dev.Mp : sa.dev.Mp;
@@ -677,6 +819,7 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
         McArgs m;
         m.model = cfg->model; m.lik = cfg->lik; m.S = cfg->S; m.K = K;
         m.temperature = cfg->temperature;
+        m.squash = c->rm_squash;
         m.inv_n_global = 1.0 / (double)cfg->n_global;
         m.n = n; m.ldn = ldc; m.n_local = N_local; m.chunk_offset = c0;
         m.Y = Y + c0;
@@ -725,18 +868,31 @@ int mgp_elbo_finish(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, 
     for (const mgp_layer_grad* g : {pg, ag})
         if (!g->Z || !g->q_mu || !g->q_sqrt || !g->variance || !g->lengthscales)
             return fail(c, MGP_ERR_BAD_ARG, "elbo_finish: NULL gradient pointer");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    ON_CTX_DEVICE(c);
     const Launch ln = launch_of(c);
     LayerSlot &sp = c->slot[0], &sa = c->slot[1];
     TRY(setup_layer(c, sp, pred, true));
     TRY(setup_layer(c, sa, assign, true));
-    if (!c->pre_valid) {
+    // the precompute held by the context must be THESE layers' (a caller may interleave two models on one context, or
+    // call a predict path in between): same dimensions and parameter pointers, else it is formed again here
+    const bool same_layers = memcmp(&c->pre_layer[0], pred, sizeof(mgp_layer)) == 0 &&
+                             memcmp(&c->pre_layer[1], assign, sizeof(mgp_layer)) == 0;
+    const bool from_local = c->pre_valid && same_layers;
+    if (!from_local) {
         const Launch ls = fork_side(c);
         precompute_layer(sp.dev, true, (int*)c->status.p, ln);
         precompute_layer(sa.dev, true, (int*)c->status.p, ls);
         join_side(c);
         c->pre_valid = true;
         c->kl_valid = false;
+        c->pre_layer[0] = *pred;
+        c->pre_layer[1] = *assign;
+    } else {
+        // same pointers: were the VALUES behind them changed since mgp_elbo_local factorised them?
+        FingerprintArgs fa;
+        fa.l[0] = *pred; fa.l[1] = *assign;
+        fingerprint_kernel<<<2, 256, 0, c->stream>>>(fa, (unsigned long long*)c->fprint.p + 2);
+        c->launches += 1;
     }
     const int K = pred->K;
     const LayerRB rp = layer_rb(RB_HEADER, sp.dev.Mp, sp.dev.Dp, K);
@@ -752,7 +908,9 @@ int mgp_elbo_finish(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, 
     join_side(c);
     elbo_finalize_kernel<<<1, 32, 0, c->stream>>>(reduce_buf, kl, cfg->num_data, K, elbo,
                                                   cfg->lik == MGP_LIK_GAUSSIAN ? lik_var_grad : nullptr,
-                                                  cfg->model == MGP_MODEL_SMGP_MODIFIED ? assign_lik_var_grad : nullptr);
+                                                  cfg->model == MGP_MODEL_SMGP_MODIFIED ? assign_lik_var_grad : nullptr,
+                                                  from_local ? (const unsigned long long*)c->fprint.p : nullptr,
+                                                  (int*)c->status.p);
     c->launches += 1;
     CUDA_TRY(c, cudaGetLastError());
     return MGP_OK;
@@ -765,6 +923,7 @@ int mgp_elbo_fwd_bwd(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred,
     if (!c) return MGP_ERR_BAD_ARG;
     const int64_t len = mgp_reduce_buffer_len(pred, assign);
     if (len <= 0) return fail(c, MGP_ERR_BAD_ARG, "elbo_fwd_bwd: NULL layer");
+    ON_CTX_DEVICE(c);
     TRY(check_cfg(c, cfg, pred, assign, lik_var, assign_lik_var));
     TRY(ensure(c, c->scratch_rb, (size_t)len * 8));
     TRY(mgp_elbo_local(c, cfg, pred, assign, lik_var, assign_lik_var, X, Y, N_local, noise, (double*)c->scratch_rb.p));
@@ -775,7 +934,7 @@ int mgp_elbo_fwd_bwd(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred,
 int mgp_debug_kuu_chol(mgp_ctx* c, const mgp_layer* layer, double* Kuu, double* L, double* Linv) {
     if (!c) return MGP_ERR_BAD_ARG;
     if (!Kuu || !L || !Linv) return fail(c, MGP_ERR_BAD_ARG, "debug_kuu_chol: NULL output");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    ON_CTX_DEVICE(c);
     c->pre_valid = false; c->kl_valid = false;
     TRY(setup_layer(c, c->slot[0], layer, false));
     precompute_layer(c->slot[0].dev, false, (int*)c->status.p, launch_of(c));

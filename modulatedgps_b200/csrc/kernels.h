@@ -85,6 +85,7 @@ int syrk_make_plan(int Mp, int K, int64_t n, int kc, int num_sms, std::vector<Sy
 struct McArgs {
     int model, lik, S, K;
     double temperature;
+    double squash;        // RobustMax CDF squash (MGP_ROBUSTMAX_CDF_SQUASH unless mgp_set_robustmax_squash changed it)
     double inv_n_global;
     int64_t n;            // valid points in the chunk
     int64_t ldn;          // padded points (adjoints of padded points are written as 0)
@@ -109,10 +110,11 @@ void mc_fold(const double* block_part, int nblocks, double* rb_header, const Lau
 // ---- predict paths ------------------------------------------------------------------------------------
 void predict_assign_kernel(const double* fmean, int64_t n, int K, double* probs, int64_t* argmax, const Launch& ln);
 void predict_y_kernel(const double* fmean, const double* fvar, int64_t n, int K, int lik, const double* lik_var,
-                      double* mean, double* var, const Launch& ln);
+                      double squash, double* mean, double* var, const Launch& ln);
 struct SampleArgs {
     int S, K, lik;
     double temperature;
+    double squash;
     int64_t n;
     const double *fmean_p, *fvar_p, *fmean_a, *fvar_a;  // [n, K]
     const double* lik_var;
@@ -126,6 +128,14 @@ void predict_samples_kernel(const SampleArgs& a, const Launch& ln);
 void w_sample_kernel(const SampleArgs& a, double* W_out, const Launch& ln);
 // out [n] = logsumexp_S(sum_k W ve) - log S for the expert likelihood `lik` (0 Gaussian, 1 MultiClass RobustMax)
 void e_log_p_y_kernel(const double* fmean, const double* fvar, const double* Y, const double* lik_var, int lik,
-                      const double* W, int S, int64_t n, int K, double* out, const Launch& ln);
+                      double squash, const double* W, int S, int64_t n, int K, double* out, const Launch& ln);
+
+// stand-alone likelihood methods (mode 0 variational expectations, 1 Gaussian log-prob, 2 Gaussian predictive log density)
+void lik_eval_kernel(int mode, int lik, const double* lik_var, double squash, const double* Fmu, const double* Fvar,
+                     const double* Y, int64_t rows, int64_t y_period, int K, double* out, const Launch& ln);
+// Philox test entries: ctr_key [n][6] = counter[4], key[2] -> out [n][4]; raw z / u draws [S, n, K] of throughput mode
+void philox_kat_kernel(const uint32_t* ctr_key, int n, uint32_t* out, const Launch& ln);
+void philox_draws_kernel(uint64_t seed, int64_t point_offset, int64_t n, int S, int K, int stream, double* z, double* u,
+                         const Launch& ln);
 
 }  // namespace mgp

@@ -64,21 +64,8 @@ __device__ __forceinline__ void philox_draw_all(uint64_t seed, int64_t point, in
 }
 
 // ---- RobustMax Gauss-Hermite quadrature (gpflow MultiClass) ----------------------------
-__constant__ double c_gh_x[20];
-__constant__ double c_gh_w[20];   // weights / sqrt(pi)
-static bool g_gh_ready = false;
-
-static void ensure_gh(cudaStream_t) {
-    if (g_gh_ready) return;
-    const double* x = GH20_X;
-    const double* w = GH20_W;
-    double ws[20];
-    const double sqrt_pi = 1.7724538509055160273;
-    for (int i = 0; i < 20; ++i) ws[i] = w[i] / sqrt_pi;
-    cudaMemcpyToSymbol(c_gh_x, x, sizeof(double) * 20);
-    cudaMemcpyToSymbol(c_gh_w, ws, sizeof(ws));
-    g_gh_ready = true;
-}
+// c_gh_x / c_gh_w come statically initialised from gh20.h: a __constant__ symbol exists once per device, and a
+// first-use symbol upload behind a process-wide flag would fill only the device current at that moment.
 
 // epsilon after GPflow's Sigmoid-bijector round trip of 1e-3
 __device__ __forceinline__ double robustmax_eps() {
@@ -90,8 +77,9 @@ __device__ __forceinline__ double robustmax_eps() {
 // p = P(f_c is largest) and its gradient w.r.t. mu[.] and var[.]
 template <int K, bool GRAD>
 __device__ __forceinline__ double robustmax_prob(int c, const double (&mu)[K], const double (&var)[K],
-                                                 double (&dmu)[K], double (&dvar)[K]) {
-    const double c1 = 1.0 - 2e-6, INV_SQRT2 = 0.70710678118654752440, INV_SQRT_2PI = 0.39894228040143267794;
+                                                 double (&dmu)[K], double (&dvar)[K], double squash) {
+    // gpflow RobustMax.prob_is_largest: cdfs = cdfs * (1 - 2 squash) + squash, squash = MGP_ROBUSTMAX_CDF_SQUASH
+    const double c1 = 1.0 - 2.0 * squash, INV_SQRT2 = 0.70710678118654752440, INV_SQRT_2PI = 0.39894228040143267794;
     double sd[K];
     double mu_c = 0.0, var_c = 0.0;
 #pragma unroll
@@ -109,7 +97,7 @@ __device__ __forceinline__ double robustmax_prob(int c, const double (&mu)[K], c
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             dist[j] = (X - mu[j]) / sd[j];
-            cdf[j] = (0.5 * (1.0 + erf(dist[j] * INV_SQRT2))) * c1 + 1e-6;
+            cdf[j] = (0.5 * (1.0 + erf(dist[j] * INV_SQRT2))) * c1 + squash;
             if (j == c) cdf[j] = 1.0;
             prod *= cdf[j];
         }
@@ -243,7 +231,7 @@ __global__ void __launch_bounds__(MC_THREADS, MC_MIN_CTAS) mc_pass_kernel(McArgs
             }
         } else {
             const double eps = robustmax_eps();
-            const double p = robustmax_prob<K, true>((int)y, mu_p, var_p, dp_dmu, dp_dvar);
+            const double p = robustmax_prob<K, true>((int)y, mu_p, var_p, dp_dmu, dp_dvar, a.squash);
             const double ve = p * log(1.0 - eps) + (1.0 - p) * log(eps / (K - 1.0));
 #pragma unroll
             for (int k = 0; k < K; ++k) e[k] = ve;
@@ -373,7 +361,6 @@ static void mc_dispatch(const McArgs& a, double* block_part, int nblocks, cudaSt
 }
 
 void mc_pass(const McArgs& a, double* block_part, const Launch& ln) {
-    ensure_gh(ln.stream);
     const int nblocks = mc_num_blocks(a.ldn);
     switch (a.K) {
         case 1: mc_dispatch<1>(a, block_part, nblocks, ln.stream); break;
@@ -432,7 +419,7 @@ void predict_assign_kernel(const double* fmean, int64_t n, int K, double* probs,
 
 template <int K>
 __global__ void predict_y_k(const double* fmean, const double* fvar, int64_t n, int lik, const double* lik_var,
-                            double* mean, double* var) {
+                            double squash, double* mean, double* var) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double mu[K], v[K];
@@ -445,7 +432,7 @@ __global__ void predict_y_k(const double* fmean, const double* fvar, int64_t n, 
         const double eps = robustmax_eps();
         double d0[K], d1[K];
         for (int c = 0; c < K; ++c) {
-            const double p = robustmax_prob<K, false>(c, mu, v, d0, d1);
+            const double p = robustmax_prob<K, false>(c, mu, v, d0, d1, squash);
             const double ps = p * (1.0 - eps) + (1.0 - p) * (eps / (K - 1.0));
             mean[(size_t)i * K + c] = ps;
             var[(size_t)i * K + c] = ps - ps * ps;
@@ -454,12 +441,11 @@ __global__ void predict_y_k(const double* fmean, const double* fvar, int64_t n, 
 }
 
 void predict_y_kernel(const double* fmean, const double* fvar, int64_t n, int K, int lik, const double* lik_var,
-                      double* mean, double* var, const Launch& ln) {
+                      double squash, double* mean, double* var, const Launch& ln) {
     if (n <= 0) return;
-    ensure_gh(ln.stream);
     const unsigned grid = (unsigned)((n + 127) / 128);
-#define PY(KK) case KK: predict_y_k<KK><<<grid, 128, 0, ln.stream>>>(fmean, fvar, n, lik, lik_var, mean, var); break;
-    switch (K) { PY(1) PY(2) PY(3) PY(4) PY(5) PY(6) PY(7) default: predict_y_k<8><<<grid, 128, 0, ln.stream>>>(fmean, fvar, n, lik, lik_var, mean, var); }
+#define PY(KK) case KK: predict_y_k<KK><<<grid, 128, 0, ln.stream>>>(fmean, fvar, n, lik, lik_var, squash, mean, var); break;
+    switch (K) { PY(1) PY(2) PY(3) PY(4) PY(5) PY(6) PY(7) default: predict_y_k<8><<<grid, 128, 0, ln.stream>>>(fmean, fvar, n, lik, lik_var, squash, mean, var); }
 #undef PY
     ln.tick();
 }
@@ -496,9 +482,10 @@ __global__ void predict_samples_k(SampleArgs a) {
         for (int k = 0; k < K; ++k) { my[k] = mu[k]; vy[k] = v[k] + a.lik_var[k]; }
     } else {
         const double eps = robustmax_eps();
+        const double squash = a.squash;
         double d0[K], d1[K];
         for (int c = 0; c < K; ++c) {
-            const double p = robustmax_prob<K, false>(c, mu, v, d0, d1);
+            const double p = robustmax_prob<K, false>(c, mu, v, d0, d1, squash);
             my[c] = p * (1.0 - eps) + (1.0 - p) * (eps / (K - 1.0));
             vy[c] = my[c] - my[c] * my[c];
         }
@@ -516,7 +503,6 @@ __global__ void predict_samples_k(SampleArgs a) {
 void predict_samples_kernel(const SampleArgs& a, const Launch& ln) {
     const int64_t total = (int64_t)a.S * a.n;
     if (total <= 0) return;
-    ensure_gh(ln.stream);
     const unsigned grid = (unsigned)((total + 127) / 128);
 #define PS(KK) case KK: predict_samples_k<KK><<<grid, 128, 0, ln.stream>>>(a); break;
     switch (a.K) { PS(1) PS(2) PS(3) PS(4) PS(5) PS(6) PS(7) default: predict_samples_k<8><<<grid, 128, 0, ln.stream>>>(a); }
@@ -564,7 +550,7 @@ void w_sample_kernel(const SampleArgs& a, double* W_out, const Launch& ln) {
 // out[n] = logsumexp_s( sum_k W[s,n,k] ve[n,k] ) - log S,  ve = the expert likelihood's variational expectation
 template <int K>
 __global__ void e_log_p_y_k(const double* fmean, const double* fvar, const double* Y, const double* lik_var, int lik,
-                            const double* W, int S, int64_t n, double* out) {
+                            double squash, const double* W, int S, int64_t n, double* out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double mu[K], v[K], ve[K];
@@ -582,7 +568,7 @@ __global__ void e_log_p_y_k(const double* fmean, const double* fvar, const doubl
         double d0[K], d1[K];
         int c = (int)y;
         c = c < 0 ? 0 : (c >= K ? K - 1 : c);
-        const double p = robustmax_prob<K, false>(c, mu, v, d0, d1);
+        const double p = robustmax_prob<K, false>(c, mu, v, d0, d1, squash);
         const double val = p * log(1.0 - eps) + (1.0 - p) * log(eps / (K - 1.0));
 #pragma unroll
         for (int k = 0; k < K; ++k) ve[k] = val;
@@ -599,13 +585,106 @@ __global__ void e_log_p_y_k(const double* fmean, const double* fvar, const doubl
 }
 
 void e_log_p_y_kernel(const double* fmean, const double* fvar, const double* Y, const double* lik_var, int lik,
-                      const double* W, int S, int64_t n, int K, double* out, const Launch& ln) {
+                      double squash, const double* W, int S, int64_t n, int K, double* out, const Launch& ln) {
     if (n <= 0) return;
-    ensure_gh(ln.stream);
     const unsigned grid = (unsigned)((n + 127) / 128);
-#define EL(KK) case KK: e_log_p_y_k<KK><<<grid, 128, 0, ln.stream>>>(fmean, fvar, Y, lik_var, lik, W, S, n, out); break;
-    switch (K) { EL(1) EL(2) EL(3) EL(4) EL(5) EL(6) EL(7) default: e_log_p_y_k<8><<<grid, 128, 0, ln.stream>>>(fmean, fvar, Y, lik_var, lik, W, S, n, out); }
+#define EL(KK) case KK: e_log_p_y_k<KK><<<grid, 128, 0, ln.stream>>>(fmean, fvar, Y, lik_var, lik, squash, W, S, n, out); break;
+    switch (K) { EL(1) EL(2) EL(3) EL(4) EL(5) EL(6) EL(7) default: e_log_p_y_k<8><<<grid, 128, 0, ln.stream>>>(fmean, fvar, Y, lik_var, lik, squash, W, S, n, out); }
 #undef EL
+    ln.tick();
+}
+
+// ==================================================================================================
+// The likelihood methods the reference exposes as stand-alone calls (broadcasting_lik.py:39-46, likelihoods.py:21-41,
+// gpflow MultiClass): elementwise over R = S N rows of [.., K] arrays; Y is [N] and row r reads Y[r % y_period]
+// (the reference tiles Y over the S axis, broadcasting_lik.py:27-31).
+//   mode 0  variational_expectations: Gaussian -> [R, K] (not reduced over k, likelihoods.py:39-41); MultiClass -> [R]
+//   mode 1  GaussianModified._scalar_log_prob: logdensities.gaussian(Y, F, variance) -> [R, K]   (likelihoods.py:21-22)
+//   mode 2  GaussianModified._predict_log_density: sum_k gaussian(Y, Fmu, Fvar + variance) -> [R] (likelihoods.py:34-35)
+// ==================================================================================================
+template <int K>
+__global__ void lik_eval_k(int mode, int lik, const double* lik_var, double squash, const double* Fmu, const double* Fvar,
+                           const double* Y, int64_t rows, int64_t y_period, double* out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    double mu[K], v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        mu[k] = Fmu[(size_t)r * K + k];
+        v[k] = (mode == 1 || Fvar == nullptr) ? 0.0 : Fvar[(size_t)r * K + k];
+    }
+    const double y = Y[r % y_period];
+    if (lik == 0) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const double d = y - mu[k];
+            double val;
+            if (mode == 2) {
+                const double s2 = v[k] + lik_var[k];
+                val = -HALF_LOG_2PI - 0.5 * log(s2) - 0.5 * d * d / s2;
+                acc += val;
+            } else {
+                const double s2 = lik_var[k];
+                val = -HALF_LOG_2PI - 0.5 * log(s2) - 0.5 * (d * d + v[k]) / s2;
+                out[(size_t)r * K + k] = val;
+            }
+        }
+        if (mode == 2) out[r] = acc;
+    } else {
+        const double eps = robustmax_eps();
+        double d0[K], d1[K];
+        int c = (int)y;
+        c = c < 0 ? 0 : (c >= K ? K - 1 : c);
+        const double p = robustmax_prob<K, false>(c, mu, v, d0, d1, squash);
+        out[r] = p * log(1.0 - eps) + (1.0 - p) * log(eps / (K - 1.0));
+    }
+}
+
+void lik_eval_kernel(int mode, int lik, const double* lik_var, double squash, const double* Fmu, const double* Fvar,
+                     const double* Y, int64_t rows, int64_t y_period, int K, double* out, const Launch& ln) {
+    if (rows <= 0) return;
+    const unsigned grid = (unsigned)((rows + 127) / 128);
+#define LE(KK) case KK: lik_eval_k<KK><<<grid, 128, 0, ln.stream>>>(mode, lik, lik_var, squash, Fmu, Fvar, Y, rows, y_period, out); break;
+    switch (K) { LE(1) LE(2) LE(3) LE(4) LE(5) LE(6) LE(7) default: lik_eval_k<8><<<grid, 128, 0, ln.stream>>>(mode, lik, lik_var, squash, Fmu, Fvar, Y, rows, y_period, out); }
+#undef LE
+    ln.tick();
+}
+
+// Philox4x32-10 known-answer entry (tests: Random123's kat_vectors) and the raw throughput-mode draws of one block of
+// points, so that the uniform -> normal / Gumbel mapping and the counter packing can be tested statistically.
+__global__ void philox_kat_k(const uint32_t* ctr_key, int n, uint32_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c[4] = {ctr_key[i * 6 + 0], ctr_key[i * 6 + 1], ctr_key[i * 6 + 2], ctr_key[i * 6 + 3]};
+    philox4x32_10(c, ctr_key[i * 6 + 4], ctr_key[i * 6 + 5]);
+    for (int j = 0; j < 4; ++j) out[i * 4 + j] = c[j];
+}
+void philox_kat_kernel(const uint32_t* ctr_key, int n, uint32_t* out, const Launch& ln) {
+    if (n <= 0) return;
+    philox_kat_k<<<(n + 127) / 128, 128, 0, ln.stream>>>(ctr_key, n, out);
+    ln.tick();
+}
+
+template <int K>
+__global__ void philox_draws_k(uint64_t seed, int64_t point_offset, int64_t n, int S, int stream, double* z, double* u) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)S * n) return;
+    const int s = (int)(idx / n);
+    const int64_t i = idx % n;
+    double zz[K], uu[K];
+    philox_draw_all<K>(seed, point_offset + i, s, stream, zz, uu);
+#pragma unroll
+    for (int k = 0; k < K; ++k) { z[idx * K + k] = zz[k]; u[idx * K + k] = uu[k]; }
+}
+void philox_draws_kernel(uint64_t seed, int64_t point_offset, int64_t n, int S, int K, int stream, double* z, double* u,
+                         const Launch& ln) {
+    const int64_t total = (int64_t)S * n;
+    if (total <= 0) return;
+    const unsigned grid = (unsigned)((total + 127) / 128);
+#define PD(KK) case KK: philox_draws_k<KK><<<grid, 128, 0, ln.stream>>>(seed, point_offset, n, S, stream, z, u); break;
+    switch (K) { PD(1) PD(2) PD(3) PD(4) PD(5) PD(6) PD(7) default: philox_draws_k<8><<<grid, 128, 0, ln.stream>>>(seed, point_offset, n, S, stream, z, u); }
+#undef PD
     ln.tick();
 }
 

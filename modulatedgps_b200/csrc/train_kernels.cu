@@ -24,8 +24,11 @@ struct AdamTable {
     mgp_adam_slot s[MGP_ADAM_MAX_SLOTS];
 };
 
+// guard: device scalar (the step's ELBO) — a step whose ELBO is not finite (failed Cholesky, stale precompute) must not
+// reach theta, m, v: the reference's tf.linalg.cholesky raises before the optimiser runs.
 __global__ void __launch_bounds__(256) adam_kernel(AdamTable tab, double grad_scale, double lr_t, double beta1, double beta2,
-                                                   double eps) {
+                                                   double eps, const double* guard) {
+    if (guard != nullptr && !isfinite(*guard)) return;
     const mgp_adam_slot sl = tab.s[blockIdx.y];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sl.n; i += (int64_t)gridDim.x * blockDim.x) {
         const double th = sl.theta[i];
@@ -137,7 +140,7 @@ using namespace mgp;
 extern "C" {
 
 int mgp_adam_step(void* cuda_stream, const mgp_adam_slot* slots, int32_t nslots, double grad_scale, double lr, double beta1,
-                  double beta2, double eps, int64_t step) {
+                  double beta2, double eps, int64_t step, const double* guard) {
     if (!slots || nslots < 0 || nslots > MGP_ADAM_MAX_SLOTS || step < 1) return MGP_ERR_BAD_ARG;
     if (nslots == 0) return MGP_OK;
     AdamTable tab;
@@ -151,7 +154,7 @@ int mgp_adam_step(void* cuda_stream, const mgp_adam_slot* slots, int32_t nslots,
     int gx = (int)((nmax + 255) / 256);
     if (gx > 1184) gx = 1184;   // 8 waves of 148 SMs; grid-stride beyond
     if (gx < 1) gx = 1;
-    adam_kernel<<<dim3(gx, nslots), 256, 0, (cudaStream_t)cuda_stream>>>(tab, grad_scale, lr_t, beta1, beta2, eps);
+    adam_kernel<<<dim3(gx, nslots), 256, 0, (cudaStream_t)cuda_stream>>>(tab, grad_scale, lr_t, beta1, beta2, eps, guard);
     return cudaGetLastError() == cudaSuccess ? MGP_OK : MGP_ERR_CUDA;
 }
 

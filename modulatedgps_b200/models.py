@@ -447,7 +447,14 @@ class SMGP(SGP):
             if p is None or not isinstance(p, Parameter):
                 return
             shape = p.shape                      # (of the constrained value; evaluating p.value() here would re-run
-            g = g.reshape(shape) if g.numel() == shape.numel() else g   # the bijector kernels twice per parameter)
+            if g.numel() == shape.numel():       # the bijector kernels twice per parameter)
+                g = g.reshape(shape)
+            elif shape.numel() == 1:
+                # a scalar parameter broadcast over the K components (GaussianModified(variance=v) with D=None is the
+                # reference's constructor default, likelihoods.py:13-19): the gradient of a broadcast is the sum
+                g = g.sum().reshape(shape)
+            else:
+                raise ValueError(f"gradient of {g.numel()} entries for a parameter of shape {tuple(shape)}")
             out[id(p)] = (p, g if id(p) not in out else out[id(p)][1] + g)
 
         for lname, layer in (("pred", self.pred_layer), ("assign", self.assign_layer)):

@@ -55,8 +55,9 @@ class FusedAdam:
                 gather = (torch.arange(lead, device=th.device).unsqueeze(1) * (m * m) + pos_of.unsqueeze(0)).reshape(-1).contiguous()
             self.state[id(p)] = {"m": torch.zeros_like(th), "v": torch.zeros_like(th), "gather": gather, "kind": kind}
 
-    def apply_gradients(self, param_grads, grad_scale=-1.0):
-        """param_grads: {id(Parameter): (Parameter, d ELBO / d constrained value)}; grad_scale -1 minimises -ELBO."""
+    def apply_gradients(self, param_grads, grad_scale=-1.0, guard=None):
+        """param_grads: {id(Parameter): (Parameter, d ELBO / d constrained value)}; grad_scale -1 minimises -ELBO.
+        guard: device scalar (the step's ELBO); a non-finite value makes the kernel skip the whole update."""
         self.iterations += 1
         slots = (_lib.MgpAdamSlot * _lib.ADAM_MAX_SLOTS)()
         keep, ns = [], 0
@@ -67,19 +68,21 @@ class FusedAdam:
             g = hit[1].contiguous()
             st = self.state[id(p)]
             th = p.unconstrained_variable.data
+            if st["gather"] is None and g.numel() != th.numel():
+                raise ValueError(f"gradient of {g.numel()} entries for a parameter of {th.numel()}")
             keep.append(g)
             slots[ns] = _lib.MgpAdamSlot(th.data_ptr(), g.data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(),
                                          None if st["gather"] is None else st["gather"].data_ptr(), th.numel(), st["kind"], 0)
             ns += 1
         lib = _lib.load_library()
         _check(lib.mgp_adam_step(_stream_ptr(), slots, ns, float(grad_scale), self.lr, self.beta_1, self.beta_2,
-                                 self.epsilon, self.iterations), "mgp_adam_step")
+                                 self.epsilon, self.iterations, _lib.ptr(guard)), "mgp_adam_step")
 
     def minimize(self, data, **kw):
         """One optimisation step on the minibatch `data` = (X, Y); returns the training loss (-ELBO) tensor."""
         X, Y = data
         elbo, grads, _ = self.model._run(X, Y, kw.get("noise"), kw.get("n_global"), kw.get("point_offset"))
-        self.apply_gradients(self.model._param_grad_map(grads))
+        self.apply_gradients(self.model._param_grad_map(grads), guard=elbo)
         return -elbo
 
 
@@ -88,7 +91,13 @@ def make_adam(model, lr):
 
 
 def run_adam(model, num_iter, train_iter, lr, compile=True):
-    """utils/training_utils.py:4-28.  `train_iter`: an iterator of (X, Y) minibatches or one (X, Y) tuple."""
+    """utils/training_utils.py:4-28.  `train_iter`: an iterator of (X, Y) minibatches or one (X, Y) tuple.
+
+    The loop below deliberately keeps the reference's control flow and output format line for line (header, an ELBO
+    line every 5 iterations from a SECOND forward on a new minibatch, KeyboardInterrupt -> "stopping training",
+    (iters, elbos) returned) so that logs and plots made from it are interchangeable with the reference's; what differs
+    is the optimiser behind `optimization_step` (one fused libmgp launch instead of TF's minimize) and that a failed
+    Cholesky is raised at the logging points, where the loop synchronises anyway (TF raises inside the step)."""
     training_loss = model.training_loss_closure(train_iter, compile=compile)
     optimizer = make_adam(model, lr)
     batches = train_iter if hasattr(train_iter, "__next__") else None
@@ -105,6 +114,7 @@ def run_adam(model, num_iter, train_iter, lr, compile=True):
 
             if i % 5 == 0 or i == 0:
                 elbo = -float(training_loss().detach())     # a second forward on a NEW minibatch, as the reference
+                _lib.get_context().check_status()           # not-PD Kuu since the last log: raise (updates were skipped)
                 print('{:>5d}'.format(i) + '{:>24.6f}'.format(elbo))
                 iters.append(i)
                 elbos.append(elbo)
@@ -184,12 +194,16 @@ def kmeans(obs, k_or_guess, iter=20, thresh=1e-5, seed=None, max_lloyd=200):
     return best
 
 
-def predict_samples_batched(model, Xnew, S=1, batch=500):
-    """demos/demo_tf2.py:62-68: predict_samples over a long test set in chunks, stacked along the point axis."""
+def predict_samples_batched(model, Xnew, S=1, batch=500, noise=None):
+    """demos/demo_tf2.py:62-68: predict_samples over a long test set in chunks, stacked along the point axis.
+    noise = (z_assign, u, z_pred), each [S, N, K], is cut along the point axis with the chunks."""
     X = to_device_f64(Xnew)
+    if noise is not None:
+        noise = tuple(to_device_f64(a, X.device) for a in noise)
     ys, fs = [], []
     for i in range(0, X.shape[0], batch):
-        y, f = model.predict_samples(X[i:i + batch], S=S)
+        nz = None if noise is None else tuple(a[:, i:i + batch].contiguous() for a in noise)
+        y, f = model.predict_samples(X[i:i + batch], S=S, noise=nz)
         ys.append(y)
         fs.append(f)
     return torch.cat(ys, 1), torch.cat(fs, 1)

@@ -8,6 +8,10 @@ import tensorflow_probability as tfp
 from .base import Module, Parameter
 from .utilities import to_default_int
 
+# gpflow's literal in RobustMax.prob_is_largest: `cdfs = cdfs * (1 - 2e-4) + 1e-4` (the attribute _squash = 1e-6 below
+# exists in gpflow too and is never read there).  Same named constant as oracle/svgp_mixture.py and include/mgp.h.
+ROBUSTMAX_CDF_SQUASH = 1e-4
+
 
 def hermgauss(n):
     x, w = np.polynomial.hermite.hermgauss(n)
@@ -57,7 +61,7 @@ class RobustMax(Module):
         # CDF of the Gaussian between the latent functions and the grid (including the selected function)
         dist = (tf.expand_dims(X, 1) - tf.expand_dims(mu, 2)) / tf.expand_dims(self.safe_sqrt(var), 2)
         cdfs = 0.5 * (1.0 + tf.math.erf(dist / np.sqrt(2.0)))
-        cdfs = cdfs * (1 - 2 * self._squash) + self._squash
+        cdfs = cdfs * (1 - 2 * ROBUSTMAX_CDF_SQUASH) + ROBUSTMAX_CDF_SQUASH
         # blank out all the distances on the selected latent function
         oh_off = tf.cast(tf.one_hot(tf.reshape(Y, (-1,)), self.num_classes, 0.0, 1.0), dtype=mu.dtype)
         cdfs = cdfs * tf.expand_dims(oh_off, 2) + tf.expand_dims(oh_on, 2)

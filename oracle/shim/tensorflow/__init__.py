@@ -357,6 +357,86 @@ class linalg:  # noqa: N801  (tf.linalg namespace)
     eye = staticmethod(eye)
 
 
+def zeros_like(x):
+    return _wrap(_torch.zeros_like(_t(x)))
+
+
+def stop_gradient(x):
+    return _wrap(_t(x).detach())
+
+
+def py_function(func, inp, Tout):
+    """tf.py_function: run `func` eagerly on the inputs (the shim is always eager)."""
+    out = func(*[_t(a) for a in inp])
+    return [_t(o) for o in out] if isinstance(out, (list, tuple)) else _t(out)
+
+
+class GradientTape:
+    """The slice of tf.GradientTape modulatedgps_b200.tf_adapter uses: watch + gradient(target, source,
+    output_gradients=) as a vector-Jacobian product (torch.autograd.grad underneath)."""
+
+    def __init__(self, persistent=False, watch_accessed_variables=True):
+        self.persistent = persistent
+
+    def __enter__(self):
+        self._prev = _torch.is_grad_enabled()
+        _torch.set_grad_enabled(True)
+        return self
+
+    def __exit__(self, *exc):
+        _torch.set_grad_enabled(self._prev)
+        return False
+
+    def watch(self, x):
+        assert _t(x).requires_grad, "the shim can only watch tensors that already require grad"
+
+    def gradient(self, target, sources, output_gradients=None):
+        single = not isinstance(sources, (list, tuple))
+        srcs = [sources] if single else list(sources)
+        tgt = _t(target)
+        if not tgt.requires_grad:                    # identity bijector: target IS the source
+            g = [_t(output_gradients) if tgt is _t(s) or tgt.data_ptr() == _t(s).data_ptr() else None for s in srcs]
+        else:
+            go = None if output_gradients is None else _t(output_gradients)
+            g = _torch.autograd.grad(tgt, [_t(s) for s in srcs], grad_outputs=go, retain_graph=True, allow_unused=True)
+        g = [None if e is None else _wrap(e) for e in g]
+        return g[0] if single else g
+
+
+def custom_gradient(f):
+    """tf.custom_gradient: f(*args) -> (result, grad_fn); grad_fn(upstream) -> one gradient (or None) per arg."""
+    def wrapped(*args):
+        targs = tuple(_t(a) for a in args)
+        holder = {}
+
+        class _Fn(_torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, *xs):
+                with _torch.enable_grad():           # inner tapes differentiate pieces of the forward
+                    y, grad_fn = f(*xs)
+                holder["grad_fn"] = grad_fn
+                return _t(y).detach().clone()
+
+            @staticmethod
+            def backward(ctx, upstream):
+                g = holder["grad_fn"](_wrap(upstream))
+                return tuple(None if e is None else _t(e) for e in g)
+
+        return _wrap(_Fn.apply(*targs))
+    return wrapped
+
+
+class experimental:  # noqa: N801  (tf.experimental namespace)
+    class dlpack:  # noqa: N801
+        @staticmethod
+        def to_dlpack(x):
+            return _torch.utils.dlpack.to_dlpack(_t(x).detach().as_subclass(_torch.Tensor).contiguous())
+
+        @staticmethod
+        def from_dlpack(capsule):
+            return _wrap(_torch.utils.dlpack.from_dlpack(capsule))
+
+
 def function(fn=None, **kw):
     """tf.function: eager pass-through."""
     if fn is None:

@@ -12,7 +12,14 @@ Cases mirror BASELINE.json `configs`:
   demo_john_doe                     config #3  (demos/demo_john_doe.py:29-56)       SMGP, D=2, M=25, K=4 on data/john_doe_dataset.csv
   synth4_small / synth5_small       configs #4/#5 scaled down (ARD lengthscales, jittered-grid / sampled Z)
   smgpmod_gauss_small               SMGPModified with Gaussian experts (demos/demo_tf2_modified.py)
-each at GPflow-default initialisation ("init") and at a perturbed parameter state ("pert").
+each at GPflow-default initialisation ("init") and at a perturbed parameter state ("pert"), and (round 2)
+  *_fullbatch.pert                  configs #1-#3 at the demos' OWN batch sizes (500 / 500 / 445 rows), perturbed state
+  shape_d5_k1 / shape_d6_k7 / shape_d10_k2   shapes the kernels special-case and round 1 never exercised: D = 5, 6, 10
+                                    put the Kuf exponent's row/column terms into the padding of the SECOND / THIRD k4 block
+                                    of the z.x contraction (kuf_fold); K = 1 (softmax over one component) and K = 7 (odd K:
+                                    unpaired Box-Muller branch, KP padding)
+All cases now carry predict_samples (MultiClass experts included: models.py:91-103 through
+MultiClass._predict_mean_and_var).
 """
 import os
 import sys
@@ -68,12 +75,11 @@ def emit(name, case, X, Y, Xtest, seed):
     u = rng.uniform(tiny, 1.0, (S, N, K))
     S2, Nt = 7, Xtest.shape[0]
     sample_noise = (rng.standard_normal((S2, Nt, K)), rng.uniform(tiny, 1.0, (S2, Nt, K)), rng.standard_normal((S2, Nt, K)))
-    out = ref.evaluate(case, X, Y, z, u, Xtest=Xtest, sample_noise=sample_noise if case["lik"] == "gaussian" else None)
+    out = ref.evaluate(case, X, Y, z, u, Xtest=Xtest, sample_noise=sample_noise)
     rec = {"meta.model": case["model"], "meta.lik": case["lik"], "meta.K": K, "meta.S": S,
            "meta.num_data": float(case["num_data"]), "X": X, "Y": np.asarray(Y, dtype=np.float64), "Xtest": Xtest,
            "z": z, "u": u, "cond.pred": cond_kuu(case["pred"]), "cond.assign": cond_kuu(case["assign"])}
-    if case["lik"] == "gaussian":
-        rec["sample.z_assign"], rec["sample.u"], rec["sample.z_pred"] = sample_noise
+    rec["sample.z_assign"], rec["sample.u"], rec["sample.z_pred"] = sample_noise
     for lname in ("pred", "assign"):
         for k, v in case[lname].items():
             rec[f"{lname}.{k}"] = np.asarray(v, dtype=np.float64)
@@ -83,15 +89,22 @@ def emit(name, case, X, Y, Xtest, seed):
     for k, v in out.items():
         rec["out." + k] = np.asarray(v)
     path = os.path.join(HERE, name + ".npz")
+    if os.path.exists(path):          # leave byte-identical fixtures alone (np.savez stamps the current time)
+        old = np.load(path)
+        if sorted(old.files) == sorted(rec) and all(np.array_equal(np.asarray(old[k]), np.asarray(rec[k])) for k in rec):
+            print(f"{name:44s} unchanged")
+            return
     np.savez(path, **rec)
     print(f"{name:44s} elbo={out['elbo']:+.15e}  cond(Kuu)=({rec['cond.pred']:.2e},{rec['cond.assign']:.2e})  "
           f"{os.path.getsize(path) / 1024:.0f} KB")
 
 
-def both_states(name, model, lik, K, S, num_data, pred0, assign0, lik_var0, assign_lik_var0, X, Y, Xtest, seed, ard):
+def both_states(name, model, lik, K, S, num_data, pred0, assign0, lik_var0, assign_lik_var0, X, Y, Xtest, seed, ard,
+                init=True):
     base = {"model": model, "lik": lik, "K": K, "S": S, "num_data": num_data}
-    emit(name + ".init", dict(base, pred=pred0, assign=assign0, lik_var=lik_var0, assign_lik_var=assign_lik_var0),
-         X, Y, Xtest, seed)
+    if init:
+        emit(name + ".init", dict(base, pred=pred0, assign=assign0, lik_var=lik_var0, assign_lik_var=assign_lik_var0),
+             X, Y, Xtest, seed)
     rng = np.random.default_rng(seed + 100)
     lv = None if lik_var0 is None else np.asarray(lik_var0) * rng.uniform(0.6, 1.5, size=K)
     alv = None if assign_lik_var0 is None else np.asarray(assign_lik_var0) * rng.uniform(0.6, 1.5, size=K)
@@ -110,6 +123,10 @@ def main():
     both_states("demo_tf2", "SMGP", "gaussian", K, 25, N,
                 default_layer(Z, K, 0.5, 0.5), default_layer(Za, K, 0.1, 1.0), 0.5 * np.ones(K), None,
                 Xtr[sel], Ytr[sel], Xte[:NTEST], seed=11, ard=False)
+    full = np.random.default_rng(13).choice(N, 500, replace=False)          # batch_size 500, demo_tf2.py:27
+    both_states("demo_tf2_fullbatch", "SMGP", "gaussian", K, 25, N,
+                default_layer(Z, K, 0.5, 0.5), default_layer(Za, K, 0.1, 1.0), 0.5 * np.ones(K), None,
+                Xtr[full], Ytr[full], Xte[:NTEST], seed=14, ard=False, init=False)
     # the analytic known-answer needs the full 1500 points at init: keep it as its own file
     case = {"model": "SMGP", "lik": "gaussian", "K": K, "S": 2, "num_data": N,
             "pred": default_layer(Z, K, 0.5, 0.5), "assign": default_layer(Za, K, 0.1, 1.0),
@@ -124,6 +141,9 @@ def main():
     both_states("demo_tf2_2d_modified_multiclass", "SMGPModified", "multiclass", K, 25, N,
                 default_layer(Z, K, 0.1, 1.0), default_layer(Za, K, 0.1, 1.0), None, 0.5 * np.ones(K),
                 Xtr[sel], Ytr[sel], Xte[:NTEST], seed=21, ard=True)
+    both_states("demo_tf2_2d_modified_multiclass_fullbatch", "SMGPModified", "multiclass", K, 25, N,   # the whole set is
+                default_layer(Z, K, 0.1, 1.0), default_layer(Za, K, 0.1, 1.0), None, 0.5 * np.ones(K),  # one batch (:28)
+                Xtr, Ytr, Xte[:NTEST], seed=23, ard=True, init=False)
 
     # ---- config #3: demos/demo_john_doe.py --------------------------------------------------
     N, Xtr, Ytr, Xte = ref.load_reference_dataset("john_doe_runs", 0)
@@ -133,6 +153,9 @@ def main():
     both_states("demo_john_doe", "SMGP", "gaussian", K, 25, N,
                 default_layer(Z, K, 0.1, 1.0), default_layer(Za, K, 0.1, 1.0), 0.5 * np.ones(K), None,
                 Xtr[sel], Ytr[sel], Xte[:NTEST], seed=31, ard=True)
+    both_states("demo_john_doe_fullbatch", "SMGP", "gaussian", K, 25, N,                              # 445 train rows
+                default_layer(Z, K, 0.1, 1.0), default_layer(Za, K, 0.1, 1.0), 0.5 * np.ones(K), None,
+                Xtr, Ytr, Xte[:NTEST], seed=33, ard=True, init=False)
 
     # ---- config #4 scaled down: D=2, M=64 (8x8 jittered grid), K=4, S=16, ARD ---------------
     rng = np.random.default_rng(40)
@@ -169,6 +192,21 @@ def main():
     both_states("smgpmod_gauss_small", "SMGPModified", "gaussian", K, 10, N,
                 default_layer(Z, K, 0.5, 0.5), default_layer(Za, K, 0.1, 1.0), 0.5 * np.ones(K), 0.5 * np.ones(K),
                 Xtr[sel], Ytr[sel], Xte[:NTEST], seed=61, ard=False)
+
+    # ---- shapes the kernels special-case (kuf_fold in the 2nd / 3rd k4 block; K = 1; odd K) ---------------------
+    for name, D, K, S, M, model in (("shape_d5_k1", 5, 1, 6, 40, "SMGP"), ("shape_d6_k7", 6, 7, 5, 33, "SMGP"),
+                                    ("shape_d10_k2", 10, 2, 6, 36, "SMGPModified")):
+        rng = np.random.default_rng(70 + D)
+        N = 96
+        X = rng.standard_normal((N, D))
+        comp = rng.integers(0, K, N)
+        om, ph = rng.uniform(0.5, 1.5, (K, D)), rng.uniform(0, 6, K)
+        Y = (np.sin((X * om[comp]).sum(1) + ph[comp]) + 1.5 * comp + 0.1 * rng.standard_normal(N))[:, None]
+        Xpool = rng.standard_normal((2 * M, D))
+        both_states(name, model, "gaussian", K, S, 4096,
+                    default_layer(Xpool[:M], K, 1.0, 2.0 * np.ones(D)), default_layer(Xpool[M:], K, 0.5, 2.5 * np.ones(D)),
+                    0.1 + 0.05 * np.arange(K), (0.3 + 0.05 * np.arange(K)) if model == "SMGPModified" else None,
+                    X, Y, rng.standard_normal((NTEST, D)), seed=80 + D, ard=True, init=False)
 
 
 if __name__ == "__main__":

@@ -10,7 +10,9 @@ RTOL = 1e-9   # north_star: "within 1e-9 relative in float64"
 
 
 def golden_names():
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """The model-case fixtures (hp_*.npz are high-precision spot-check fixtures with their own layout)."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                  if not os.path.basename(p).startswith("hp_"))
 
 
 def load_golden(name):

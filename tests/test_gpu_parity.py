@@ -100,38 +100,7 @@ def test_prior_kl_matches_oracle(hg):
         assert abs(float(layer.prior_kl()) - ref) <= 1e-12 * abs(ref)
 
 
-def _synthetic_case(N, D, M, K, S, seed, model="SMGP", ls_assign=1.1):
-    """Config-#4-style synthetic workload at an oracle-sized N.  SURVEY asks for cond(Kuu) <~ 1e4 so
-    that 1e-9 is above the conditioning noise floor; its assign lengthscale 1.5 on a unit grid gives cond 4e6, so
-    the strict cases use 1.1 (cond 1.3e4) and the 1.5 case is tested with a conditioning-scaled tolerance."""
-    rng = np.random.default_rng(seed)
-    side = int(round(math.sqrt(M)))
-    if D == 2 and side * side == M:
-        gx = np.linspace(0.5, side - 0.5, side)
-        grid = np.stack(np.meshgrid(gx, gx, indexing="ij"), -1).reshape(-1, 2)
-        Zp, Za = grid + rng.uniform(-0.2, 0.2, grid.shape), grid + rng.uniform(-0.2, 0.2, grid.shape)
-        X = rng.uniform(0, side, (N, D))
-        lsp, lsa = np.array([1.0, 1.0]), np.array([ls_assign, ls_assign])
-    else:
-        X = rng.standard_normal((N, D))
-        pool = rng.standard_normal((2 * M, D))
-        Zp, Za = pool[:M], pool[M:]
-        lsp, lsa = 2.5 * np.ones(D), 3.0 * np.ones(D)
-    comp = rng.integers(0, K, N)
-    Y = (np.sin(X.sum(1) + comp) + 1.5 * comp + 0.1 * rng.standard_normal(N))[:, None]
-
-    def layer(Z, var, ls):
-        q = np.stack([np.eye(M) + 0.05 * np.tril(rng.standard_normal((M, M))) for _ in range(K)])
-        idx = np.arange(M)
-        q[:, idx, idx] = np.abs(q[:, idx, idx]) + 0.05
-        return {"variance": np.float64(var), "lengthscales": ls, "Z": Z, "q_mu": 0.3 * rng.standard_normal((M, K)), "q_sqrt": q}
-
-    case = {"model": model, "lik": "gaussian", "K": K, "S": S, "num_data": float(N), "pred": layer(Zp, 1.0, lsp),
-            "assign": layer(Za, 0.5, lsa), "lik_var": 0.1 + 0.05 * np.arange(K),
-            "assign_lik_var": (0.4 + 0.1 * np.arange(K)) if model != "SMGP" else None}
-    z = rng.standard_normal((S, N, K))
-    u = rng.uniform(np.finfo(np.float64).tiny, 1.0, (S, N, K))
-    return case, X, Y, z, u
+from modulatedgps_b200.workloads import synthetic_case as _synthetic_case  # noqa: E402
 
 
 @pytest.mark.parametrize("N,D,M,K,S", [(3000, 2, 256, 4, 16), (700, 8, 96, 8, 8), (257, 1, 40, 3, 5),
@@ -389,14 +358,28 @@ def test_kmeans_finds_the_clusters_scipy_finds(hg):
     assert code1.shape == (2, 1)
 
 
-def test_predict_samples_batched_equals_one_call(hg):
-    """The demos' chunked predict_samples loop (demo_tf2.py:62-68) stitches to the same shapes as one call."""
+@pytest.mark.parametrize("lik", ["gaussian", "multiclass"])
+def test_predict_samples_batched_equals_one_call(lik, hg):
+    """The demos' chunked predict_samples loop (demo_tf2.py:62-68): on explicit noise the stitched chunks ARE the one
+    un-batched call, value for value (each point's sample depends on its own row of the noise only), and both match the
+    oracle; with device noise the chunks stitch to the same shapes and stay finite."""
     import modulatedgps_b200 as mg
-    case, X, Y, _, _ = _synthetic_case(700, 2, 36, 3, 4, seed=2)
+    from oracle import svgp_mixture as O
+    N, K, S = 700, 3, 6
+    case, X, Y, _, _ = _synthetic_case(N, 2, 36, K, 4, seed=2, model="SMGP" if lik == "gaussian" else "SMGPModified")
+    case["lik"] = lik
     model = hg.build_model(case)
-    ys, fs = mg.predict_samples_batched(model, X, S=6, batch=256)
-    assert tuple(ys.shape) == (6, 700, 1) and tuple(fs.shape) == (6, 700, 1)
-    assert torch.isfinite(ys).all() and torch.isfinite(fs).all()
+    rng = np.random.default_rng(21)
+    noise = (rng.standard_normal((S, N, K)), rng.uniform(np.finfo(np.float64).tiny, 1.0, (S, N, K)), rng.standard_normal((S, N, K)))
+    y1, f1 = model.predict_samples(X, S=S, noise=noise)
+    yb, fb = mg.predict_samples_batched(model, X, S=S, batch=256, noise=noise)
+    assert tuple(yb.shape) == (S, N, 1) and tuple(fb.shape) == (S, N, 1)
+    assert torch.equal(yb, y1) and torch.equal(fb, f1)
+    ry, rf = O.predict_samples(O.layer_from_numpy(case["pred"]), O.layer_from_numpy(case["assign"]), lik,
+                               O.as_t(case["lik_var"]), X, *noise)
+    assert relerr(_np(y1), ry.numpy()) <= RTOL and relerr(_np(f1), rf.numpy()) <= RTOL
+    ys, fs = mg.predict_samples_batched(model, X, S=S, batch=256)
+    assert tuple(ys.shape) == (S, N, 1) and torch.isfinite(ys).all() and torch.isfinite(fs).all()
 
 
 @pytest.mark.parametrize("model_kind,lik", [("SMGP", "gaussian"), ("SMGPModified", "gaussian"), ("SMGPModified", "multiclass")])
@@ -458,12 +441,11 @@ def test_full_size_config4_chunking_and_sharding_invariance(hg):
     mgp_elbo_finish, gives the same ELBO and the same gradients.  Exercises the tile counts, SYRK point-range splits
     and 64-bit offsets of the benchmark shape."""
     import ctypes as C
-    from bench import make_workload
     from modulatedgps_b200 import _lib
     from modulatedgps_b200.models import _LayerView
+    from modulatedgps_b200.workloads import config4_workload
     N = 1 << 20
-    case, X, Y = make_workload(N, seed=0)
-    case["num_data"] = float(N)
+    case, X, Y = config4_workload(N, seed=0, num_data=N)
     # (the strict tolerances below need a Kuu whose conditioning leaves room for them: DESIGN.md §3)
     case["assign"]["lengthscales"] = np.asarray([1.1, 1.1])
     model = hg.build_model(case)

@@ -1,0 +1,373 @@
+"""GPU tests added in round 2: the gaps the round-1 review listed (VERDICT.md "what's weak" 2-4, 9).
+
+  * the throughput-mode noise generator: Philox4x32-10 known answers (Random123 kat_vectors) and the distribution of the
+    z / u draws the fused Monte-Carlo pass consumes (moments, tails, KS, independence of the Box-Muller pair);
+  * the likelihood method surface (BroadcastingLikelihood.variational_expectations / predict_mean_and_var,
+    GaussianModified._variational_expectations / _predict_mean_and_var / _scalar_log_prob / _predict_log_density,
+    MultiClass._variational_expectations / _predict_mean_and_var) against the oracle's formulas;
+  * the stale-precompute guard across mgp_elbo_local / mgp_elbo_finish: two models interleaved on one context, and
+    parameters changed in place between the two calls;
+  * a scalar likelihood variance with K > 1 (the reference's constructor default), Adam's non-finite guard;
+  * the RobustMax squash override (the A/B of DESIGN.md §3) and the 60-digit conditional spot check.
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import RTOL, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def hg():
+    from tests import helpers_gpu
+    return helpers_gpu
+
+
+def _case(*a, **kw):
+    from modulatedgps_b200.workloads import synthetic_case
+    return synthetic_case(*a, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Philox
+# ---------------------------------------------------------------------------------------------------------------
+def test_philox4x32_10_known_answers():
+    """Random123 kat_vectors, philox4x32 10 rounds: (counter, key) -> output."""
+    from modulatedgps_b200 import _lib
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    ctx = _lib.get_context()
+    inp = torch.tensor(np.array([c + k for c, k, _ in kat], dtype=np.uint32).view(np.int32), device="cuda")
+    out = torch.zeros(len(kat), 4, dtype=torch.int32, device="cuda")
+    ctx.check(ctx.lib.mgp_debug_philox(ctx.handle, C.c_void_p(inp.data_ptr()), len(kat), C.c_void_p(out.data_ptr())))
+    got = out.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, np.array([o for _, _, o in kat], dtype=np.uint32)), [[hex(v) for v in r] for r in got]
+
+
+def _draws(seed, N, S, K, stream=0, offset=0):
+    from modulatedgps_b200 import _lib
+    ctx = _lib.get_context()
+    z = torch.empty(S, N, K, dtype=torch.float64, device="cuda")
+    u = torch.empty(S, N, K, dtype=torch.float64, device="cuda")
+    nz = _lib.MgpNoise(None, None, seed, offset)
+    ctx.check(ctx.lib.mgp_debug_noise(ctx.handle, C.byref(nz), N, S, K, stream, _lib.ptr(z), _lib.ptr(u)))
+    return z, u
+
+
+@pytest.mark.parametrize("K", [1, 4, 7])
+def test_throughput_mode_noise_has_the_right_distribution(K):
+    """>= 1e7 draws per array of what mc_pass consumes in throughput mode (the benchmarked path): z ~ N(0, 1),
+    u ~ U(0, 1), all components / samples / points independent.  Bounds are ~5 sigma of the estimator at this sample
+    size, so a correct generator fails with probability < 1e-5 and a biased one (wrong Box-Muller scale, 32-bit
+    truncation of u, components sharing a counter) fails by orders of magnitude."""
+    from scipy import stats
+    N, S = 1 << 18, 16 if K < 7 else 8
+    z, u = _draws(12345, N, S, K)
+    n = z.numel()
+    assert n >= 1e7 / 2.5 and bool(torch.isfinite(z).all())
+    se = 1.0 / math.sqrt(n)
+    zz = z.reshape(-1)
+    assert abs(float(zz.mean())) < 5 * se
+    assert abs(float(zz.var()) - 1.0) < 5 * math.sqrt(2.0) * se
+    assert abs(float((zz ** 3).mean())) < 5 * math.sqrt(15.0) * se                      # skewness
+    assert abs(float((zz ** 4).mean()) - 3.0) < 5 * math.sqrt(96.0) * se               # kurtosis
+    for t in (2.0, 3.0, 4.0):                                                          # two-sided tail mass
+        p = 2 * stats.norm.sf(t)
+        assert abs(float((zz.abs() > t).double().mean()) - p) < 5 * math.sqrt(p / n) + 1e-12
+    uu = u.reshape(-1)
+    assert float(uu.min()) > 0.0 and float(uu.max()) < 1.0                             # log(-log u) stays finite
+    assert abs(float(uu.mean()) - 0.5) < 5 * se / math.sqrt(12.0)
+    assert abs(float(uu.var()) - 1.0 / 12.0) < 5 * se / math.sqrt(180.0)
+    assert float((uu < 1e-6).double().mean()) < 1e-6 + 5 * math.sqrt(1e-6 / n)         # 53-bit mantissa: no mass at 0
+    sub = slice(0, 2_000_000)
+    assert stats.kstest(zz[sub].cpu().numpy(), "norm").pvalue > 1e-4
+    assert stats.kstest(uu[sub].cpu().numpy(), "uniform").pvalue > 1e-4
+    # independence: components (k, k + 1 share one Box-Muller radius: cosine / sine branches), z vs u, samples, points
+    pairs = []
+    if K > 1:
+        pairs += [(z[..., 0], z[..., 1]), (z[..., 0] ** 2, z[..., 1] ** 2), (u[..., 0], u[..., 1]), (z[..., K - 1], u[..., 0])]
+    pairs += [(z[..., 0], u[..., 0]), (z[0], z[1]), (z[:, :-1], z[:, 1:]), (u[:, :-1], u[:, 1:])]
+    for a, b in pairs:
+        a, b = a.reshape(-1), b.reshape(-1)
+        r = float(((a - a.mean()) * (b - b.mean())).mean() / (a.std() * b.std()))
+        assert abs(r) < 5 / math.sqrt(a.numel()), r
+    # the stream index and the seed select different, uncorrelated streams; the point offset shifts the same stream
+    z1, _ = _draws(12345, 4096, 2, K, stream=1)
+    z2, _ = _draws(12346, 4096, 2, K)
+    z3, _ = _draws(12345, 4096 - 100, 2, K, offset=100)
+    assert not torch.equal(z1, z[:2, :4096]) and not torch.equal(z2, z[:2, :4096])
+    assert torch.equal(z3, z[:2, 100:4096])
+
+
+def test_w_sample_in_philox_mode_is_the_documented_function_of_the_draws(hg):
+    """mgp_w_sample without explicit noise == the oracle's relaxed one-hot evaluated on mgp_debug_noise's draws for the
+    same (seed, offset): the throughput path uses exactly the stream the distribution test examines."""
+    from modulatedgps_b200 import _lib
+    from oracle import svgp_mixture as O
+    N, K, S = 300, 3, 5
+    case, X, Y, _, _ = _case(N, 2, 36, K, S, seed=4)
+    model = hg.build_model(case)
+    model.seed, model._step = 9, 0
+    W = model.W_dist(X).sample(1)[0].reshape(S, N, K)
+    z, u = _draws((9 << 20) + 1, N, S, K)
+    mu_a, var_a = O.conditional(O.as_t(X), O.layer_from_numpy(case["assign"]))
+    Wref = O.relaxed_onehot_weights(mu_a, var_a, z.cpu(), u.cpu())
+    assert np.abs(W.cpu().numpy() - Wref.numpy()).max() <= 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# likelihood method surface
+# ---------------------------------------------------------------------------------------------------------------
+def test_gaussian_modified_methods_match_the_reference_formulas():
+    import modulatedgps_b200 as mg
+    rng = np.random.default_rng(0)
+    S, N, K = 5, 37, 4
+    Fmu, Fvar = rng.standard_normal((S, N, K)), rng.uniform(0.05, 2.0, (S, N, K))
+    Y = rng.standard_normal((N, 1))
+    var = rng.uniform(0.2, 1.5, K)
+    lik = mg.GaussianModified(variance=1.0, D=K)
+    lik.variance.assign(var.reshape(1, K))
+    ve_ref = -0.5 * np.log(2 * np.pi) - 0.5 * np.log(var) - 0.5 * ((Y[None] - Fmu) ** 2 + Fvar) / var   # likelihoods.py:39-41
+    b = mg.BroadcastingLikelihood(lik)
+    ve = b.variational_expectations([], Fmu, Fvar, Y)
+    assert tuple(ve.shape) == (S, N, K) and relerr(np.asarray(ve), ve_ref) <= 1e-13
+    # the pass-through call the reference makes: Y expanded to [1, N, 1] (broadcasting_lik.py:22-24)
+    ve2 = lik._variational_expectations([], Fmu, Fvar, Y[None])
+    assert torch.equal(ve2, ve)
+    mean, v = b.predict_mean_and_var([], Fmu, Fvar)
+    assert np.array_equal(np.asarray(mean), Fmu) and relerr(np.asarray(v), Fvar + var) <= 1e-15   # likelihoods.py:31-32
+    lp = lik._scalar_log_prob([], Fmu, Y[None])
+    assert relerr(np.asarray(lp), -0.5 * np.log(2 * np.pi) - 0.5 * np.log(var) - 0.5 * (Y[None] - Fmu) ** 2 / var) <= 1e-13
+    pld = lik._predict_log_density([], Fmu, Fvar, Y[None])
+    s2 = Fvar + var
+    assert tuple(pld.shape) == (S, N)
+    assert relerr(np.asarray(pld), (-0.5 * np.log(2 * np.pi) - 0.5 * np.log(s2) - 0.5 * (Y[None] - Fmu) ** 2 / s2).sum(-1)) <= 1e-13
+    assert np.array_equal(np.asarray(lik._conditional_mean([], Fmu)), Fmu)
+    assert np.array_equal(np.asarray(lik._conditional_variance([], Fmu)), np.broadcast_to(var, Fmu.shape))
+    # the reference's default constructor: ONE variance shared by all components
+    lik1 = mg.GaussianModified(variance=0.7)
+    ve1 = lik1._variational_expectations([], Fmu, Fvar, Y[None])
+    assert relerr(np.asarray(ve1), -0.5 * np.log(2 * np.pi) - 0.5 * np.log(0.7) - 0.5 * ((Y[None] - Fmu) ** 2 + Fvar) / 0.7) <= 1e-13
+    with pytest.raises(ValueError):
+        b.variational_expectations([], Fmu, Fvar, Y[:-1])
+
+
+@pytest.mark.parametrize("K", [2, 3, 5])
+def test_multiclass_methods_match_the_oracle(K):
+    import modulatedgps_b200 as mg
+    from oracle import svgp_mixture as O
+    rng = np.random.default_rng(K)
+    S, N = 3, 41
+    Fmu, Fvar = rng.standard_normal((S, N, K)), rng.uniform(1e-12, 1.5, (S, N, K))
+    Fvar[0, :3] = 0.0                                           # below safe_sqrt's 1e-10 clip
+    Y = rng.integers(0, K, (N, 1)).astype(np.float64)
+    lik = mg.MultiClass(K, invlink=mg.RobustMax(K))
+    b = mg.BroadcastingLikelihood(lik)
+    ve = b.variational_expectations([], Fmu, Fvar, Y)
+    assert tuple(ve.shape) == (S, N, 1)                         # broadcasting_lik.py:26-37: reshaped to [S, N, -1]
+    Yt = np.tile(Y[None], (S, 1, 1)).reshape(S * N, 1)
+    ref = O.multiclass_ve(O.as_t(Yt), O.as_t(Fmu.reshape(S * N, K)), O.as_t(Fvar.reshape(S * N, K))).numpy()
+    assert relerr(np.asarray(ve).reshape(-1), ref) <= 1e-12
+    mean, var = b.predict_mean_and_var([], Fmu, Fvar)
+    rm, rv = O.multiclass_predict_mean_and_var(O.as_t(Fmu.reshape(S * N, K)), O.as_t(Fvar.reshape(S * N, K)))
+    assert relerr(np.asarray(mean).reshape(S * N, K), rm.numpy()) <= 1e-12
+    assert relerr(np.asarray(var).reshape(S * N, K), rv.numpy()) <= 1e-12
+
+
+def test_robustmax_squash_override_matches_the_oracle_at_both_values(hg):
+    """The A/B knob of DESIGN.md §3: with mgp_set_robustmax_squash(1e-6) the kernels reproduce the oracle evaluated with
+    1e-6, with the default they reproduce the 1e-4 goldens; the two ELBOs differ where the test can see it."""
+    from modulatedgps_b200 import _lib
+    from oracle import svgp_mixture as O
+    case, g = load_golden("demo_tf2_2d_modified_multiclass.pert")
+    model = hg.build_model(case)
+    ctx = _lib.get_context()
+    e_default, _ = model.elbo_and_grads(g["X"], g["Y"], noise=(g["z"], g["u"]))
+    assert abs(float(e_default) - float(g["out.elbo"])) <= RTOL * abs(float(g["out.elbo"]))
+    saved = O.ROBUSTMAX_CDF_SQUASH
+    try:
+        O.ROBUSTMAX_CDF_SQUASH = 1e-6
+        ctx.set_robustmax_squash(1e-6)
+        e6, g6 = model.elbo_and_grads(g["X"], g["Y"], noise=(g["z"], g["u"]))
+        ref, rg = O.elbo_and_grads(case["model"], case["lik"], O.layer_from_numpy(case["pred"]), O.layer_from_numpy(case["assign"]),
+                                   None, O.as_t(case["assign_lik_var"]), g["X"], g["Y"], g["z"], g["u"], case["num_data"])
+    finally:
+        O.ROBUSTMAX_CDF_SQUASH = saved
+        ctx.set_robustmax_squash(_lib.ROBUSTMAX_CDF_SQUASH)
+    assert abs(float(e6) - ref) <= RTOL * abs(ref)
+    assert relerr(g6["pred.q_mu"].cpu().numpy(), rg["pred.q_mu"]) <= RTOL
+    assert abs(float(e6) - float(e_default)) > 1e-7 * abs(ref)
+    with pytest.raises(_lib.MgpError):
+        ctx.set_robustmax_squash(0.5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# precompute guard across the two-phase C-ABI
+# ---------------------------------------------------------------------------------------------------------------
+def _two_phase(ctx, model, X, Y, noise, between=None):
+    from modulatedgps_b200 import _lib
+    from modulatedgps_b200.models import _LayerView
+    pv, av = _LayerView(model.pred_layer), _LayerView(model.assign_layer)
+    K, S, N = pv.K, int(model.num_samples), X.shape[0]
+    cfg = _lib.MgpElboCfg(model._model_kind, model.likelihood.kind, S, 0, float(model.temperature), float(model.num_data), N)
+    likv = model.likelihood.component_variances(K)
+    z, u = (torch.as_tensor(a, device="cuda").contiguous() for a in noise)
+    nz = _lib.MgpNoise(z.data_ptr(), u.data_ptr(), 0, 0)
+    rb = torch.empty(int(ctx.lib.mgp_reduce_buffer_len(C.byref(pv.struct), C.byref(av.struct))), dtype=torch.float64, device="cuda")
+    ctx.check(ctx.lib.mgp_elbo_local(ctx.handle, C.byref(cfg), C.byref(pv.struct), C.byref(av.struct), _lib.ptr(likv), None,
+                                     _lib.ptr(X), _lib.ptr(Y), N, C.byref(nz), _lib.ptr(rb)))
+
+    def finish():
+        pg, pgs = pv.grad_buffers()
+        ag, ags = av.grad_buffers()
+        elbo = torch.empty(1, dtype=torch.float64, device="cuda")
+        glik = torch.zeros(K, dtype=torch.float64, device="cuda")
+        ctx.check(ctx.lib.mgp_elbo_finish(ctx.handle, C.byref(cfg), C.byref(pv.struct), C.byref(av.struct), _lib.ptr(likv), None,
+                                          _lib.ptr(rb), _lib.ptr(elbo), C.byref(pgs), C.byref(ags), _lib.ptr(glik), None))
+        grads = {f"pred.{k}": v for k, v in pg.items()}
+        grads.update({f"assign.{k}": v for k, v in ag.items()})
+        grads["lik_var"] = glik
+        return elbo, grads
+
+    return finish, (pv, av, z, u, likv, rb)
+
+
+def test_two_models_interleaved_on_one_context(hg):
+    """local(A), local(B), finish(A), finish(B) on ONE context: finish must not run A's Cholesky backward on B's
+    factorisation (round 1 trusted a bare `pre_valid` flag).  Different M on purpose."""
+    from modulatedgps_b200 import _lib
+    ctx = _lib.get_context()
+    ca, Xa, Ya, za, ua = _case(500, 2, 64, 4, 6, seed=31)
+    cb, Xb, Yb, zb, ub = _case(400, 2, 36, 4, 6, seed=32)
+    ma, mb = hg.build_model(ca), hg.build_model(cb)
+    ea, ga = ma.elbo_and_grads(Xa, Ya, noise=(za, ua))
+    eb, gb = mb.elbo_and_grads(Xb, Yb, noise=(zb, ub))
+    ga, gb = {k: v.clone() for k, v in ga.items()}, {k: v.clone() for k, v in gb.items()}
+    dev = lambda a: torch.as_tensor(a, device="cuda").contiguous()
+    fin_a, keep_a = _two_phase(ctx, ma, dev(Xa), dev(Ya).reshape(-1), (za, ua))
+    fin_b, keep_b = _two_phase(ctx, mb, dev(Xb), dev(Yb).reshape(-1), (zb, ub))
+    e1, g1 = fin_a()
+    e2, g2 = fin_b()
+    e3, g3 = fin_a()                                           # and again, after B's finish replaced the factorisation
+    ctx.check_status()
+    for (e, g), (er, gr) in (((e1, g1), (ea, ga)), ((e2, g2), (eb, gb)), ((e3, g3), (ea, ga))):
+        assert abs(float(e) - float(er)) <= 1e-12 * abs(float(er))
+        for k in ("pred.Z", "pred.q_sqrt", "pred.lengthscales", "assign.Z", "assign.q_mu", "assign.variance", "lik_var"):
+            assert relerr(g[k].cpu().numpy(), gr[k].cpu().numpy().reshape(g[k].shape)) <= 1e-11, k
+
+
+def test_parameters_changed_between_local_and_finish_are_reported(hg):
+    import modulatedgps_b200 as mg
+    from modulatedgps_b200 import _lib
+    ctx = _lib.get_context()
+    case, X, Y, z, u = _case(300, 2, 36, 3, 4, seed=33)
+    model = hg.build_model(case)
+    dev = lambda a: torch.as_tensor(a, device="cuda").contiguous()
+    finish, keep = _two_phase(ctx, model, dev(X), dev(Y).reshape(-1), (z, u))
+    e_ok, _ = finish()
+    ctx.check_status()
+    assert math.isfinite(float(e_ok))
+    finish, keep = _two_phase(ctx, model, dev(X), dev(Y).reshape(-1), (z, u))
+    keep[0].q_mu.mul_(1.0 + 1e-12)                             # an optimiser step in place, between the two phases
+    e_bad, _ = finish()
+    assert math.isnan(float(e_bad))
+    with pytest.raises(mg.MgpError) as err:
+        ctx.check_status()
+    assert err.value.code == _lib.MGP_ERR_STALE_PRECOMPUTE
+    ctx.check_status()                                         # the flag is cleared once reported
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training-side fixes
+# ---------------------------------------------------------------------------------------------------------------
+def test_scalar_likelihood_variance_with_several_components(hg):
+    """GaussianModified(variance=v) with D=None (the reference's default) broadcasts ONE variance over the K components:
+    its gradient is the SUM of the per-component gradients, on the autograd path and in FusedAdam."""
+    import copy
+    import modulatedgps_b200 as mg
+    from oracle import svgp_mixture as O
+    case, X, Y, z, u = _case(200, 2, 25, 3, 4, seed=41)
+    case["lik_var"] = 0.3 * np.ones(3)
+
+    def build():
+        lik = mg.GaussianModified(variance=0.3)
+        assert tuple(lik.variance.shape) == ()
+        mk = lambda p: mg.SVGPModified(kernel=mg.SquaredExponential(float(p["variance"]), p["lengthscales"]), likelihood=lik,
+                                       inducing_variable=p["Z"], num_latent_gps=3, q_mu=p["q_mu"], q_sqrt=np.tril(p["q_sqrt"]))
+        return lik, mg.SMGP(lik, mk(case["pred"]), mk(case["assign"]), K=3, num_samples=4, num_data=case["num_data"])
+
+    lik, model = build()
+    ref, rg = O.elbo_and_grads("SMGP", "gaussian", O.layer_from_numpy(case["pred"]), O.layer_from_numpy(case["assign"]),
+                               O.as_t(case["lik_var"]), None, X, Y, z, u, case["num_data"])
+    loss = model._training_loss((X, Y), noise=(z, u))
+    loss.backward()
+    th = lik.variance.unconstrained_variable
+    expect = -rg["lik_var"].sum() * float(torch.sigmoid(th.detach()))
+    assert tuple(th.grad.shape) == tuple(th.shape)
+    assert abs(float(th.grad) - expect) <= 1e-9 * abs(expect)
+    # one fused Adam step moves theta by -lr * sign(g) (first step of Adam), with g the SUMMED gradient
+    lik2, model2 = build()
+    th2 = lik2.variance.unconstrained_variable
+    before = float(th2.detach())
+    mg.FusedAdam(model2, 0.01).minimize((X, Y), noise=(z, u))
+    step = float(th2.detach()) - before
+    assert abs(step + 0.01 * np.sign(expect)) <= 1e-6, (step, expect)
+
+
+def test_adam_skips_the_update_when_the_elbo_is_not_finite(hg):
+    """A failed Cholesky gives NaN ELBO and gradients; the fused update must leave theta, m, v untouched (no host sync
+    involved) and run_adam / check_status must raise where the reference's tf.linalg.cholesky would."""
+    import modulatedgps_b200 as mg
+    from modulatedgps_b200 import _lib
+    case, X, Y, z, u = _case(64, 2, 36, 3, 4, seed=4)
+    case["pred"]["variance"] = np.float64(1e12)                 # jitter drowns: Kuu + 1e-6 I is numerically singular
+    case["pred"]["Z"][1] = case["pred"]["Z"][0]
+    model = hg.build_model(case)
+    opt = mg.FusedAdam(model, 0.01)
+    before = [v.detach().clone() for v in model.trainable_variables]
+    loss = opt.minimize((X, Y), noise=(z, u))
+    assert not math.isfinite(float(loss))
+    for a, b in zip(before, model.trainable_variables):
+        assert torch.equal(a, b.detach())
+    for st in opt.state.values():
+        assert float(st["m"].abs().sum()) == 0.0 and float(st["v"].abs().sum()) == 0.0
+    with pytest.raises(mg.NotPositiveDefiniteError):
+        _lib.get_context().check_status()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 60-digit spot check at the bench's conditioning
+# ---------------------------------------------------------------------------------------------------------------
+def test_conditional_against_60_digit_arithmetic(hg):
+    """tests/golden/hp_conditional.npz (mpmath, 60 digits) for config #4's ASSIGN layer as benchmarked (lengthscale 1.5,
+    cond(Kuu) ~ 3e6): who is right when the float64 oracle and the float64 kernel disagree at 1e-9?  Both must sit within
+    a small multiple of eps * cond of the 60-digit value, and the kernel (explicit L^-1, DMMA accumulation order) must not
+    be more than 10x further from it than the oracle's triangular solves."""
+    import modulatedgps_b200 as mg
+    from oracle import svgp_mixture as O
+    d = np.load(os.path.join(ROOT, "tests", "golden", "hp_conditional.npz"))
+    p = {k: d["layer." + k] for k in ("variance", "lengthscales", "Z", "q_mu", "q_sqrt")}
+    K = p["q_mu"].shape[1]
+    lik = mg.GaussianModified(variance=1.0, D=K)
+    layer = mg.SVGPModified(kernel=mg.SquaredExponential(float(p["variance"]), p["lengthscales"]), likelihood=lik,
+                            inducing_variable=p["Z"], num_latent_gps=K, q_mu=p["q_mu"], q_sqrt=np.tril(p["q_sqrt"]))
+    fm, fv = layer.predict_f(d["X"])
+    om, ov = O.conditional(O.as_t(d["X"]), O.layer_from_numpy(p))
+    cond = float(np.linalg.cond(O.kuu(O.layer_from_numpy(p)).numpy()))
+    floor = np.finfo(np.float64).eps * cond
+    errs = {"kernel.fmean": relerr(np.asarray(fm), d["fmean"]), "kernel.fvar": relerr(np.asarray(fv), d["fvar"]),
+            "oracle.fmean": relerr(om.numpy(), d["fmean"]), "oracle.fvar": relerr(ov.numpy(), d["fvar"])}
+    print("60-digit spot check, cond(Kuu) = %.3g, eps*cond = %.3g: %s" % (cond, floor, errs))
+    for k, e in errs.items():
+        assert e <= floor, (k, e, floor)
+    assert errs["kernel.fmean"] <= 10 * max(errs["oracle.fmean"], 1e-15)
+    assert errs["kernel.fvar"] <= 10 * max(errs["oracle.fvar"], 1e-15)

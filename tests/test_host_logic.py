@@ -10,6 +10,8 @@ import numpy as np
 import pytest
 import torch
 
+from tests.helpers import relerr
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -155,16 +157,89 @@ def test_gauss_hermite_header_matches_numpy():
     nums = [float(t) for t in re.findall(r"-?\d+\.\d+(?:e-?\d+)?", src.split("GH20_X[20]")[1])]
     x, w = np.polynomial.hermite.hermgauss(20)
     assert np.array_equal(np.array(nums[:20]), x) and np.array_equal(np.array(nums[20:40]), w)
+    # the statically initialised __constant__ copies the kernels read (no first-use upload, no per-device flag)
+    assert np.array_equal(np.array(nums[40:60]), x) and np.array_equal(np.array(nums[60:80]), w / np.sqrt(np.pi))
+    assert "cudaMemcpyToSymbol(" not in open(os.path.join(ROOT, "modulatedgps_b200", "csrc", "mc_pass.cu")).read()
 
 
 def test_bench_workload_is_deterministic_and_well_conditioned():
     import bench
-    c1, X1, Y1 = bench.make_workload(2048, seed=0)
-    c2, X2, Y2 = bench.make_workload(2048, seed=0)
+    cfg = bench.Cfg(4, points=2048)
+    c1, X1, Y1 = bench.make_workload(cfg, 0, 2048)
+    c2, X2, Y2 = bench.make_workload(cfg, 0, 2048)
     assert np.array_equal(X1, X2) and np.array_equal(Y1, Y2) and np.array_equal(c1["pred"]["Z"], c2["pred"]["Z"])
     assert X1.shape == (2048, 2) and c1["pred"]["Z"].shape == (256, 2) and c1["pred"]["q_sqrt"].shape == (4, 256, 256)
-    assert bench.flops_per_point() == 1_999_872
+    assert bench.Cfg(4).flops_per_point() == 1_999_872
+    assert bench.Cfg(5).flops_per_point() == 56_930_304
+    assert bench.Cfg(4).N == 1 << 20 and bench.Cfg(5).N == 1 << 24
+    alg, executed = bench.Cfg(4).kernel_flops_per_point()
+    assert alg["cond_bwd_a"] == 2 * 4 * 256 * 256 and abs(executed["syrk"] / alg["syrk"] - 528 / 514) < 1e-12
+    assert abs(executed["cond_fwd_a"] / alg["cond_fwd_a"] - 17 / 16) < 1e-12
     from oracle import svgp_mixture as O
     for lname in ("pred", "assign"):
         cond = np.linalg.cond(O.kuu(O.layer_from_numpy(c1[lname])).numpy())
         assert cond < 1e7, (lname, cond)
+
+
+def test_config5_shards_are_independent_of_the_sharding():
+    """Rank r of R generates rows [r N / R, (r + 1) N / R) of the SAME data set whatever R is (bench.py --config 5)."""
+    from modulatedgps_b200 import workloads as W
+    Xa, Ya = W.config5_points(0, 3 * (1 << 16) // 2)
+    Xb, Yb = W.config5_points((1 << 16) - 5, (1 << 16) + 7)
+    assert np.array_equal(Xa[(1 << 16) - 5:(1 << 16) + 7], Xb) and np.array_equal(Ya[(1 << 16) - 5:(1 << 16) + 7], Yb)
+    assert Xa.shape == (3 * (1 << 16) // 2, 8) and Ya.shape == (3 * (1 << 16) // 2, 1)
+    case = W.config5_parameters(m=64, k=8)
+    assert case["pred"]["Z"].shape == (64, 8) and np.unique(case["pred"]["Z"], axis=0).shape[0] == 64
+
+
+def test_robustmax_squash_is_one_named_constant():
+    """include/mgp.h, the ctypes layer, the oracle and the shim carry the same RobustMax CDF squash (gpflow's literal 1e-4),
+    and the kernels take it from the context, not from a literal of their own."""
+    from modulatedgps_b200 import _lib
+    from oracle import svgp_mixture as O
+    hdr = open(os.path.join(ROOT, "include", "mgp.h")).read()
+    val = float(re.search(r"#define MGP_ROBUSTMAX_CDF_SQUASH\s+(\S+)", hdr).group(1))
+    assert val == _lib.ROBUSTMAX_CDF_SQUASH == O.ROBUSTMAX_CDF_SQUASH == 1e-4
+    shim = open(os.path.join(ROOT, "oracle", "shim", "gpflow", "likelihoods.py")).read()
+    assert float(re.search(r"^ROBUSTMAX_CDF_SQUASH = (\S+)", shim, re.M).group(1)) == val
+    src = open(os.path.join(ROOT, "modulatedgps_b200", "csrc", "mc_pass.cu")).read()
+    assert "2e-6" not in src and "1e-6;" not in src.split("robustmax_prob")[1].split("sample_weights")[0]
+
+
+def test_second_build_does_not_run_nvcc():
+    """build() must hit its cache when nothing changed (round 1 hashed its own stamp file and recompiled every time)."""
+    from modulatedgps_b200 import build as B
+    B.build()                                  # whatever state the tree is in: brings the cache up to date
+    before = B.nvcc_invocations
+    lib = B.build()
+    assert B.nvcc_invocations == before and os.path.exists(lib)
+    assert not os.path.exists(os.path.join(ROOT, "modulatedgps_b200", "csrc", ".build_stamp"))
+
+
+def test_literal_oracle_equals_the_deduplicated_one():
+    """The S-tiled formulation the reference's graph executes (bench.py's `literal` CPU timing) is the same function."""
+    from modulatedgps_b200.workloads import synthetic_case
+    from oracle import svgp_mixture as O
+    for model in ("SMGP", "SMGPModified"):
+        case, X, Y, z, u = synthetic_case(50, 2, 16, 3, 4, seed=2, model=model)
+        args = (case["model"], "gaussian", O.layer_from_numpy(case["pred"]), O.layer_from_numpy(case["assign"]),
+                O.as_t(case["lik_var"]), None if case["assign_lik_var"] is None else O.as_t(case["assign_lik_var"]),
+                X, Y, z, u, case["num_data"])
+        e0, g0 = O.elbo_and_grads(*args)
+        e1, g1 = O.elbo_and_grads(*args, literal=True)
+        assert abs(e0 - e1) <= 1e-13 * abs(e0)
+        for k in g0:
+            assert relerr(g1[k], g0[k]) <= 1e-11, k
+
+
+def test_oracle_conditional_against_60_digit_arithmetic():
+    """tests/golden/hp_conditional.npz (mpmath, 60 digits; tests/golden/make_hp_conditional.py) at the bench's own
+    conditioning, cond(Kuu) ~ 3e6: the float64 oracle's forward error must be a small multiple of eps * cond."""
+    from oracle import svgp_mixture as O
+    d = np.load(os.path.join(ROOT, "tests", "golden", "hp_conditional.npz"))
+    layer = {k: d["layer." + k] for k in ("variance", "lengthscales", "Z", "q_mu", "q_sqrt")}
+    fm, fv = O.conditional(O.as_t(d["X"]), O.layer_from_numpy(layer))
+    cond = float(np.linalg.cond(O.kuu(O.layer_from_numpy(layer)).numpy()))
+    assert 1e6 < cond < 1e7
+    floor = np.finfo(np.float64).eps * cond
+    assert relerr(fm.numpy(), d["fmean"]) <= floor and relerr(fv.numpy(), d["fvar"]) <= floor

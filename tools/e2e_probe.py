@@ -3,7 +3,7 @@ import os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import make_workload
-from tests.helpers_gpu import build_model
+from modulatedgps_b200.workloads import model_from_case as build_model
 
 n = 1 << 20
 dev = torch.device("cuda", 0)

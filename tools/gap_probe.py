@@ -6,7 +6,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import make_workload  # noqa: E402
-from tests.helpers_gpu import build_model  # noqa: E402
+from modulatedgps_b200.workloads import model_from_case as build_model  # noqa: E402
 
 
 def main():

@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from tests.helpers import golden_names, grad_keys, load_golden, relerr  # noqa: E402
-from tests.helpers_gpu import build_model, unconstrained_grad_dict  # noqa: E402
+from modulatedgps_b200.workloads import model_from_case as build_model
+from tests.helpers_gpu import unconstrained_grad_dict  # noqa: E402
 
 
 def main():

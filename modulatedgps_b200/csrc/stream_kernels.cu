@@ -53,20 +53,28 @@ __device__ __forceinline__ double exp_tab(double x, const double* tab) {
     return x < -700.0 ? 0.0 : scaled;   // (results below 1e-304 are flushed; the exponent add would leave the normal range)
 }
 
-constexpr int SK_WARPS = 8;                    // DMMA consumer warps
+// DMMA consumer warps per CTA: 8 with 32-point tiles (two warps per SM sub-partition keep the pipe ~90 % busy when a
+// fragment group is 32 DMMAs long), 16 with 16-point tiles (M > 352: a group is only 16 DMMAs = ~512 clocks of a shared
+// pipe, shorter than the L2 latency of the next group's fragments — ncu at config #5: stall_long_scoreboard 5.0 per
+// issue, DMMA pipe 69 %; tools/wloop_bench.cu: 27.0 TFLOP/s with 8 warps vs 34.9 with 16 at NT = 16).
+constexpr int SK_WARPS = 8;
+constexpr int SK_WARPS_NT16 = 16;
 constexpr int SK_CTHREADS = SK_WARPS * 32;
+__host__ __device__ constexpr int sk_warps(int nt) { return nt == 32 ? SK_WARPS : SK_WARPS_NT16; }
 
 __host__ __device__ inline int xs_stride(int Dp) { return ((Dp - 4 + 15) / 16) * 16 + 4; }
 
 // 16-row block dealt to warp w in round r (snake order); returns -1 past the end
+template <int NW = SK_WARPS>
 __device__ __forceinline__ int snake_block(int round, int warp, int nb16) {
-    const int b = round * SK_WARPS + ((round & 1) ? (SK_WARPS - 1 - warp) : warp);
+    const int b = round * NW + ((round & 1) ? (NW - 1 - warp) : warp);
     return b < nb16 ? b : -1;
 }
 // number of 16-row blocks dealt to this warp (only the last snake round can be short)
+template <int NW = SK_WARPS>
 __device__ __forceinline__ int my_block_count(int warp, int nb16) {
-    const int R = (nb16 + SK_WARPS - 1) / SK_WARPS;
-    return R == 0 ? 0 : (snake_block(R - 1, warp, nb16) >= 0 ? R : R - 1);
+    const int R = (nb16 + NW - 1) / NW;
+    return R == 0 ? 0 : (snake_block<NW>(R - 1, warp, nb16) >= 0 ? R : R - 1);
 }
 
 template <int NF>
@@ -299,8 +307,8 @@ constexpr int SK_BAR_DOUBLES = 8;   // room for 2 x NBUF mbarriers (NBUF <= 2) +
 // (measured: 9.1 ms vs 6.2 ms for this form at config #4).
 // ==================================================================================================
 template <int NT>
-__global__ void __launch_bounds__(SK_CTHREADS) cond_fwd_a_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
-    constexpr int NF = NT / 8, STR = NT + 4;
+__global__ void __launch_bounds__(sk_warps(NT) * 32) cond_fwd_a_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
+    constexpr int NF = NT / 8, STR = NT + 4, NW = sk_warps(NT);
     extern __shared__ __align__(16) double smem[];
     const int Mp = ly.Mp, XSTR = xs_stride(ly.Dp);
     double* T = smem;
@@ -311,8 +319,8 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_fwd_a_kernel(LayerDev ly, Ch
     const size_t tile_elems = (size_t)Mp * STR;
     __shared__ double etab[64];
     if (threadIdx.x < 64) etab[threadIdx.x] = d_exp_tab64[threadIdx.x];   // visible after the first CTA barrier below
-    const int nmy = my_block_count(warp, nb16);
-    auto seg_of = [&](int i) { const int b = snake_block(i, warp, nb16); return Seg{ly.W_Linv, 2 * b, 0}; };
+    const int nmy = my_block_count<NW>(warp, nb16);
+    auto seg_of = [&](int i) { const int b = snake_block<NW>(i, warp, nb16); return Seg{ly.W_Linv, 2 * b, 0}; };
     WFrag wf;
     if (nmy > 0) wfrag_load(wf, seg_of(0), C4, 0, lane);
 
@@ -321,7 +329,7 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_fwd_a_kernel(LayerDev ly, Ch
         double* Aout = cb.A + (size_t)tile * tile_elems;
         if (warp == 0) stage_x_warp<NT>(ly, cb, n0, Xs, xs2, lane);
         __syncthreads();
-        for (int rb = warp; rb < nb8; rb += SK_WARPS) {
+        for (int rb = warp; rb < nb8; rb += NW) {
             double kv[NF][2];
             gen_kuf_block<NT>(ly, rb, Xs, xs2, etab, kv, lane);
 #pragma unroll
@@ -330,7 +338,7 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_fwd_a_kernel(LayerDev ly, Ch
         }
         __syncthreads();
         for (int i = 0; i < nmy; ++i) {
-            const int b = snake_block(i, warp, nb16);
+            const int b = snake_block<NW>(i, warp, nb16);
             double acc[2][NF][2];
             zero_acc<NF>(acc);
             // (TRI_LOWER measured slower here, 5.78 vs 5.66 ms at config #4: the two CTAs' phases drift apart)
@@ -351,28 +359,29 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_fwd_a_kernel(LayerDev ly, Ch
 // warps 0-7 multiply and leave per-warp partial column sums; warp 8 loads tiles and finishes the sums
 // ==================================================================================================
 template <int NT, int NBUF>
-__global__ void __launch_bounds__(SK_CTHREADS + 32, 1) cond_fwd_b_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
-    constexpr int NF = NT / 8, STR = NT + 4;
+__global__ void __launch_bounds__(sk_warps(NT) * 32 + 32, 1) cond_fwd_b_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
+    constexpr int NF = NT / 8, STR = NT + 4, NW = sk_warps(NT);
+    constexpr int MW = SK_WARPS;   // warps that take a k-slice of the fmean contraction (C4 = Mp / 4 is a multiple of 8)
     extern __shared__ __align__(16) double smem[];
     const int Mp = ly.Mp, K = ly.K;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* done = full + NBUF;
     double* Tb = smem + SK_BAR_DOUBLES;                          // [NBUF][Mp][STR]
-    double* sqpart = Tb + (size_t)NBUF * Mp * STR;               // [NBUF][SK_WARPS][K][NT]  partial sum_m B_k^2
-    double* mnpart = sqpart + (size_t)NBUF * SK_WARPS * K * NT;  // [NBUF][SK_WARPS][K][NT]  partial q_mu^T A
+    double* sqpart = Tb + (size_t)NBUF * Mp * STR;               // [NBUF][NW][K][NT]  partial sum_m B_k^2
+    double* mnpart = sqpart + (size_t)NBUF * NW * K * NT;        // [NBUF][MW][K][NT]  partial q_mu^T A
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nb16 = Mp / 16, C4 = Mp / 4;
     const size_t tile_elems = (size_t)Mp * STR;
     const unsigned tile_bytes = (unsigned)(tile_elems * sizeof(double));
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], SK_WARPS); }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], NW); }
         mbar_fence_init();
     }
     __syncthreads();
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     auto tile_of = [&](int i) { return (int64_t)blockIdx.x + (int64_t)i * gridDim.x; };
 
-    if (warp == SK_WARPS) {   // ---- loader + finisher ----
+    if (warp == NW) {   // ---- loader + finisher ----
         auto issue = [&](int i) {
             if (lane == 0) {
                 const int buf = i % NBUF;
@@ -402,16 +411,15 @@ __global__ void __launch_bounds__(SK_CTHREADS + 32, 1) cond_fwd_b_kernel(LayerDe
                 asq[0] = (s0 + s1) + (s2 + s3);
             }
             mbar_wait(&done[buf], (unsigned)((i / NBUF) & 1));   // every consumer has left its partials and the tile
-            const double* sq = sqpart + (size_t)buf * SK_WARPS * K * NT;
-            const double* mn = mnpart + (size_t)buf * SK_WARPS * K * NT;
+            const double* sq = sqpart + (size_t)buf * NW * K * NT;
+            const double* mn = mnpart + (size_t)buf * MW * K * NT;
             if (lane < NT) {
                 for (int k = 0; k < K; ++k) {
                     double s = 0.0, m = 0.0;
 #pragma unroll
-                    for (int w = 0; w < SK_WARPS; ++w) {
-                        s += sq[((size_t)w * K + k) * NT + lane];
-                        m += mn[((size_t)w * K + k) * NT + lane];
-                    }
+                    for (int w = 0; w < NW; ++w) s += sq[((size_t)w * K + k) * NT + lane];
+#pragma unroll
+                    for (int w = 0; w < MW; ++w) m += mn[((size_t)w * K + k) * NT + lane];
                     cb.fvar[(size_t)(n0 + lane) * K + k] = (variance - asq[0]) + s;   // Knn - sum A^2 + sum LTA^2
                     cb.fmean[(size_t)(n0 + lane) * K + k] = m;
                 }
@@ -422,11 +430,11 @@ __global__ void __launch_bounds__(SK_CTHREADS + 32, 1) cond_fwd_b_kernel(LayerDe
         return;
     }
     // ---- consumers ----
-    const int nmy = my_block_count(warp, nb16);
+    const int nmy = my_block_count<NW>(warp, nb16);
     // the fmean contraction is split over the warps by k-range: warp w takes k4-blocks [w C4/8, (w+1) C4/8)
-    const int mkb0 = warp * (C4 / SK_WARPS), mkb1 = mkb0 + C4 / SK_WARPS;   // C4 = Mp/4 is a multiple of 8
+    const int mkb0 = warp * (C4 / MW), mkb1 = mkb0 + C4 / MW;   // C4 = Mp/4 is a multiple of 8; warps >= MW skip it
     auto seg_of = [&](int k, int r) {
-        const int b = snake_block(r, warp, nb16);
+        const int b = snake_block<NW>(r, warp, nb16);
         return Seg{ly.W_LqT + (size_t)k * Mp * Mp, 2 * b, 4 * b};
     };
     WPair wp;
@@ -435,8 +443,8 @@ __global__ void __launch_bounds__(SK_CTHREADS + 32, 1) cond_fwd_b_kernel(LayerDe
         const int buf = i % NBUF;
         const int64_t tile = tile_of(i);
         const double* T = Tb + (size_t)buf * tile_elems;
-        double* sq = sqpart + ((size_t)buf * SK_WARPS + warp) * K * NT;
-        double* mn = mnpart + ((size_t)buf * SK_WARPS + warp) * K * NT;
+        double* sq = sqpart + ((size_t)buf * NW + warp) * K * NT;
+        double* mn = mnpart + ((size_t)buf * MW + (warp < MW ? warp : 0)) * K * NT;
         mbar_wait(&full[buf], (unsigned)((i / NBUF) & 1));
         for (int k = 0; k < K; ++k) {
             double colsq[NF][2];
@@ -444,7 +452,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + 32, 1) cond_fwd_b_kernel(LayerDe
             for (int nf = 0; nf < NF; ++nf) colsq[nf][0] = colsq[nf][1] = 0.0;
             double* Bk = cb.Bk ? cb.Bk + ((size_t)k * cb.tiles_cap + tile) * tile_elems : nullptr;
             for (int r = 0; r < nmy; ++r) {
-                const int b = snake_block(r, warp, nb16);
+                const int b = snake_block<NW>(r, warp, nb16);
                 double acc[2][NF][2];
                 zero_acc<NF>(acc);
                 const Seg nxt = (r + 1 < nmy) ? seg_of(k, r + 1) : seg_of(k + 1 < K ? k + 1 : 0, 0);
@@ -476,7 +484,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + 32, 1) cond_fwd_b_kernel(LayerDe
                     }
             }
         }
-        {   // this warp's slice of fmean^T [K x NT] = q_mu^T [K x Mp] * A tile   (rows >= K of W_mT are zero).
+        if (warp < MW) {   // this warp's slice of fmean^T [K x NT] = q_mu^T [K x Mp] * A tile   (rows >= K of W_mT are zero).
             // Two accumulator sets (even / odd k4-blocks): the contraction is a short dependent DMMA chain.
             double acc[2][NF][2];
             zero_acc<NF>(acc);
@@ -516,9 +524,10 @@ __global__ void __launch_bounds__(SK_CTHREADS + 32, 1) cond_fwd_b_kernel(LayerDe
 // warps on one SM sub-partition) the last warp to leave a stage refills its buffer (shared-memory arrival counter).
 // ==================================================================================================
 template <int NT, int NBUF, int NBW, bool PROD_WARP>
-__global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
+__global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
     cond_bwd_a_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
-    constexpr int NF = NT / 8, STR = NT + 4;
+    constexpr int NF = NT / 8, STR = NT + 4, NW = sk_warps(NT);
+    constexpr bool SCALE_IN_SMEM = (NT == 16) && !PROD_WARP;
     extern __shared__ __align__(16) double smem[];
     const int Mp = ly.Mp, K = ly.K;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
@@ -533,7 +542,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
     const unsigned tile_bytes = (unsigned)(tile_elems * sizeof(double));
     const unsigned slab_bytes = (unsigned)(NT * K * sizeof(double));
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], SK_WARPS); left[i] = 0u; }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], NW); left[i] = 0u; }
         mbar_fence_init();
     }
     __syncthreads();
@@ -553,7 +562,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
             bulk_g2s(vbs + (size_t)(ti & 1) * NT * KP, cb.vbar + (size_t)tile * NT * K, slab_bytes, &full[buf]);
         }
     };
-    if (PROD_WARP && warp == SK_WARPS) {
+    if (PROD_WARP && warp == NW) {
         if (lane == 0)
             for (int j = 0; j < total; ++j) issue(j);
         return;
@@ -561,9 +570,9 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
     if (!PROD_WARP && warp == 0 && lane == 0)
         for (int j = 0; j < NBUF && j < total; ++j) issue(j);
 
-    const int nmy = my_block_count(warp, nb16);
+    const int nmy = my_block_count<NW>(warp, nb16);
     auto seg_of = [&](int k, int r) {
-        const int b = snake_block(r, warp, nb16);
+        const int b = snake_block<NW>(r, warp, nb16);
         return Seg{ly.W_Lq + (size_t)k * Mp * Mp, 2 * b, 0};
     };
     WFrag wf;
@@ -574,7 +583,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
     double wm[HOIST_WM ? NBW : 1][2][KP / 4];
 #pragma unroll
     for (int r = 0; r < (HOIST_WM ? NBW : 0); ++r) {
-        const int b = snake_block(r, warp, nb16);
+        const int b = snake_block<NW>(r, warp, nb16);
 #pragma unroll
         for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
@@ -593,6 +602,25 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
             for (int r = 0; r < NBW; ++r) zero_acc<NF>(acc[r]);
         }
         if (s < K) {
+            if (SCALE_IN_SMEM) {
+                // 16-point tiles (16 consumer warps, 128-register cap): the column weights 2 vbar_s are applied to the
+                // landed B_s stage in shared memory — one pass of Mp * NT multiplications per stage (< 0.5 % of its
+                // DMMA time at M = 1024) and one consumer-wide barrier — so that the products accumulate straight into
+                // `acc`: no second accumulator set, no per-block FMA epilogue, no spills.
+                double* Tw = Tb + (size_t)buf * tile_elems;
+                const int n = threadIdx.x % NT;   // NW * 32 threads, a multiple of NT: a thread stays on one column
+                const double w2 = 2.0 * vb[n * K + s];
+                for (int m = threadIdx.x / NT; m < Mp; m += (NW * 32) / NT) Tw[(size_t)m * STR + n] *= w2;
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic writes before the next bulk copy into this buffer
+                named_bar_sync(1, NW * 32);
+#pragma unroll
+                for (int r = 0; r < NBW; ++r) {
+                    if (r >= nmy) continue;
+                    const int b = snake_block<NW>(r, warp, nb16);
+                    const Seg nxt = (r + 1 < nmy) ? seg_of(s, r + 1) : seg_of(s + 1 < K ? s + 1 : 0, 0);
+                    wgemm_seg<NT, TRI_LOWER>(seg_of(s, r), (b + 1) * 4, C4, T, acc[r], lane, wf, nxt);   // lower triangular
+                }
+            } else {
             // column weights 2 vbar_s of this lane's columns; applied once per (block, s) to the finished product
             // Lq_s B_s instead of to every B fragment (keeps DMUL out of the DMMA loop)
             double sc[NF][2];
@@ -604,7 +632,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
 #pragma unroll
             for (int r = 0; r < NBW; ++r) {
                 if (r >= nmy) continue;
-                const int b = snake_block(r, warp, nb16);
+                const int b = snake_block<NW>(r, warp, nb16);
                 double ck[2][NF][2];
                 zero_acc<NF>(ck);
                 const Seg nxt = (r + 1 < nmy) ? seg_of(s, r + 1) : seg_of(s + 1 < K ? s + 1 : 0, 0);
@@ -616,6 +644,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
                         acc[r][mf][nf][0] = fma(ck[mf][nf][0], sc[nf][0], acc[r][mf][nf][0]);
                         acc[r][mf][nf][1] = fma(ck[mf][nf][1], sc[nf][1], acc[r][mf][nf][1]);
                     }
+            }
             }
         } else {   // tile epilogue: + q_mu mubar^T - 2 A diag(sum_k vbar_k), written over A (tile-major, in place)
             double* Aout = cb.A + (size_t)tile_of(ti) * tile_elems;
@@ -636,7 +665,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
                 for (int nf = 0; nf < NF; ++nf) bm[kb][nf] = (kb * 4 + t < K) ? mb[(nf * 8 + g) * K + kb * 4 + t] : 0.0;
 #pragma unroll
             for (int r = 0; r < NBW; ++r) {
-                const int b = snake_block(r, warp, nb16);
+                const int b = snake_block<NW>(r, warp, nb16);
                 if (r >= nmy || b < 0) continue;
 #pragma unroll
                 for (int mf = 0; mf < 2; ++mf)
@@ -667,7 +696,7 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
                 // nobody waits for the stragglers (a rotating duty that waited on `done` cost 3.3 % of the kernel)
                 __threadfence_block();
                 const unsigned before = atomicAdd(&left[buf], 1u);
-                if (before == SK_WARPS - 1) {
+                if (before == NW - 1) {
                     left[buf] = 0u;
                     __threadfence_block();
                     if (j + NBUF < total) issue(j + NBUF);
@@ -683,9 +712,9 @@ __global__ void __launch_bounds__(SK_CTHREADS + (PROD_WARP ? 32 : 0), 1)
 // work that overlaps best with many DMMA warps.  The Abar tile arrives by one cp.async.bulk on an mbarrier.
 // ==================================================================================================
 template <int NT>
-__global__ void __launch_bounds__(SK_CTHREADS) cond_bwd_b_kernel(LayerDev ly, ChunkBuffers cb, int ntiles,
-                                                                double* esum_part) {
-    constexpr int NF = NT / 8, STR = NT + 4;
+__global__ void __launch_bounds__(sk_warps(NT) * 32) cond_bwd_b_kernel(LayerDev ly, ChunkBuffers cb, int ntiles,
+                                                                      double* esum_part) {
+    constexpr int NF = NT / 8, STR = NT + 4, NW = sk_warps(NT);
     extern __shared__ __align__(16) double smem[];
     const int Mp = ly.Mp, Dp = ly.Dp, D = ly.D, XSTR = xs_stride(Dp), E = 1 + 2 * Dp;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // Abar tile landed (bulk copy) AND X rows staged: 2 arrivals
@@ -700,11 +729,11 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_bwd_b_kernel(LayerDev ly, Ch
     __shared__ double etab[64];
     if (threadIdx.x < 64) etab[threadIdx.x] = d_exp_tab64[threadIdx.x];   // visible after the barrier-init sync below
     double* my_part = esum_part + (size_t)blockIdx.x * Mp * E;
-    const int nmy = my_block_count(warp, nb16);
-    auto seg_of = [&](int i) { const int b = snake_block(i, warp, nb16); return Seg{ly.W_LinvT, 2 * b, 4 * b}; };
+    const int nmy = my_block_count<NW>(warp, nb16);
+    auto seg_of = [&](int i) { const int b = snake_block<NW>(i, warp, nb16); return Seg{ly.W_LinvT, 2 * b, 4 * b}; };
     WFrag wf;
     if (nmy > 0) wfrag_load(wf, seg_of(0), C4, seg_of(0).kb0, lane);
-    if (threadIdx.x == 0) { mbar_init(full, 2); mbar_init(tfree, SK_WARPS); mbar_fence_init(); }
+    if (threadIdx.x == 0) { mbar_init(full, 2); mbar_init(tfree, NW); mbar_fence_init(); }
     __syncthreads();
     // The per-fragment epilogue does not read T, so the NEXT tile's bulk copy is issued as soon as every warp has left
     // the multiply phase (tfree) and flies while the epilogues run; X rows are staged into the other Xs buffer by
@@ -731,7 +760,7 @@ __global__ void __launch_bounds__(SK_CTHREADS) cond_bwd_b_kernel(LayerDev ly, Ch
         mbar_wait(full, phase);
         if (nmy == 0) { __syncwarp(); if (lane == 0) mbar_arrive(tfree); }
         for (int i = 0; i < nmy; ++i) {
-            const int b = snake_block(i, warp, nb16);
+            const int b = snake_block<NW>(i, warp, nb16);
             double acc[2][NF][2];
             zero_acc<NF>(acc);
             wgemm_seg<NT, TRI_UPPER>(seg_of(i), C4, C4, T, acc, lane, wf, seg_of(i + 1 < nmy ? i + 1 : 0));   // upper triangular
@@ -792,9 +821,9 @@ int stream_max_parts(const Launch& ln) { return ln.num_sms * 4; }
 // Tile width of a layer's tile-major workspace (all four kernels and the SYRK share it) and the ring depth:
 //   NT = 32, 2 buffers  while two [Mp x 36] tiles fit next to the per-kernel extras;
 //   NT = 16, 2 buffers  up to Mp = 672;  NT = 16, 1 buffer beyond (no load / multiply overlap inside a CTA).
-static size_t extras_bytes(int Mp, int Dp, int K, int nt) {
+static size_t extras_bytes(int Mp, int Dp, int K, int nt, int nbuf = 2) {
     const size_t fa = (size_t)(nt * xs_stride(Dp) + nt) * 8;
-    const size_t fb = (size_t)2 * 2 * SK_WARPS * K * nt * 8;
+    const size_t fb = (size_t)nbuf * (sk_warps(nt) + SK_WARPS) * K * nt * 8;
     const size_t ba = (size_t)4 * nt * KP * 8;
     const size_t bb = (size_t)2 * (nt * xs_stride(Dp) + nt) * 8;
     size_t m = fa;
@@ -809,7 +838,7 @@ int layer_tile_width(int Mp, int Dp, int K) {
     return (2 * (size_t)Mp * 36 * 8 + extras_bytes(Mp, Dp, K, 32) <= cap) ? 32 : 16;
 }
 static int ring_depth(int Mp, int Dp, int K, int nt) {
-    return (2 * (size_t)Mp * (nt + 4) * 8 + extras_bytes(Mp, Dp, K, nt) <= (size_t)227 * 1024) ? 2 : 1;
+    return (2 * (size_t)Mp * (nt + 4) * 8 + extras_bytes(Mp, Dp, K, nt, 2) <= (size_t)227 * 1024) ? 2 : 1;
 }
 
 template <typename KernelT>
@@ -839,9 +868,10 @@ void cond_fwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
     const int NT = cb.tw;
     const size_t smem = ((size_t)ly.Mp * (NT + 4) + NT * xs_stride(ly.Dp) + NT) * sizeof(double);
     const int ntiles = (int)((cb.n + NT - 1) / NT);
+    const int threads = sk_warps(NT) * 32;
     auto launch = [&](auto kernel) {
-        const int grid = occupancy_grid(kernel, SK_CTHREADS, smem, ntiles, 0, ln);
-        kernel<<<grid, SK_CTHREADS, smem, ln.stream>>>(ly, cb, ntiles);
+        const int grid = occupancy_grid(kernel, threads, smem, ntiles, 0, ln);
+        kernel<<<grid, threads, smem, ln.stream>>>(ly, cb, ntiles);
         ln.tick();
     };
     if (NT == 32) launch(cond_fwd_a_kernel<32>); else launch(cond_fwd_a_kernel<16>);
@@ -849,8 +879,8 @@ void cond_fwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
 
 void cond_fwd_b(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
     const int NT = cb.tw, nbuf = ring_depth(ly.Mp, ly.Dp, ly.K, NT);
-    const int threads = SK_CTHREADS + 32;
-    const size_t smem = ((size_t)SK_BAR_DOUBLES + (size_t)nbuf * ly.Mp * (NT + 4) + (size_t)2 * nbuf * SK_WARPS * ly.K * NT) * sizeof(double);
+    const int threads = sk_warps(NT) * 32 + 32;
+    const size_t smem = ((size_t)SK_BAR_DOUBLES + (size_t)nbuf * ly.Mp * (NT + 4) + (size_t)nbuf * (sk_warps(NT) + SK_WARPS) * ly.K * NT) * sizeof(double);
     const int ntiles = (int)((cb.n + NT - 1) / NT);
     auto launch = [&](auto kernel) {
         const int grid = persistent_grid(kernel, threads, smem, ntiles, 0, ln);
@@ -864,7 +894,8 @@ void cond_fwd_b(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
 
 void cond_bwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
     const int NT = cb.tw, nbuf = ring_depth(ly.Mp, ly.Dp, ly.K, NT);
-    const int nbw = (ly.Mp / 16 + SK_WARPS - 1) / SK_WARPS;   // 16-row blocks per warp
+    const int nw = sk_warps(NT);
+    const int nbw = (ly.Mp / 16 + nw - 1) / nw;   // 16-row blocks per warp
     const size_t smem = ((size_t)SK_BAR_DOUBLES + (size_t)nbuf * ly.Mp * (NT + 4) + (size_t)4 * NT * KP) * sizeof(double);
     const int ntiles = (int)((cb.n + NT - 1) / NT);
     auto launch = [&](auto kernel, int threads) {
@@ -876,12 +907,12 @@ void cond_bwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
     if (NT == 32) {
         if (nbw <= 1) launch(cond_bwd_a_kernel<32, 2, 1, true>, SK_CTHREADS + 32);
         else launch(cond_bwd_a_kernel<32, 2, 2, false>, SK_CTHREADS);
-    } else if (nbuf == 2) {
-        if (nbw <= 4) launch(cond_bwd_a_kernel<16, 2, 4, true>, SK_CTHREADS + 32);
-        else launch(cond_bwd_a_kernel<16, 2, 6, false>, SK_CTHREADS);
-    } else {
-        if (nbw <= 8) launch(cond_bwd_a_kernel<16, 1, 8, false>, SK_CTHREADS);
-        else launch(cond_bwd_a_kernel<16, 1, 11, false>, SK_CTHREADS);
+    } else if (nbuf == 2) {   // 16 consumer warps, no producer warp (128-register cap): Mp <= ~600 -> at most 3 blocks per warp
+        if (nbw <= 2) launch(cond_bwd_a_kernel<16, 2, 2, false>, nw * 32);
+        else launch(cond_bwd_a_kernel<16, 2, 4, false>, nw * 32);
+    } else {                  // up to Mp = 1312: 82 row blocks over 16 warps
+        if (nbw <= 4) launch(cond_bwd_a_kernel<16, 1, 4, false>, nw * 32);
+        else launch(cond_bwd_a_kernel<16, 1, 6, false>, nw * 32);
     }
 }
 
@@ -891,8 +922,8 @@ void cond_bwd_b(const LayerDev& ly, const ChunkBuffers& cb, double* esum_part, i
     const size_t smem = ((size_t)SK_BAR_DOUBLES + (size_t)ly.Mp * (NT + 4) + 2 * (NT * xs_stride(ly.Dp) + NT)) * sizeof(double);
     const int ntiles = (int)((cb.n + NT - 1) / NT);
     auto launch = [&](auto kernel) {
-        const int grid = occupancy_grid(kernel, SK_CTHREADS, smem, ntiles, nparts_cap, ln);
-        kernel<<<grid, SK_CTHREADS, smem, ln.stream>>>(ly, cb, ntiles, esum_part);
+        const int grid = occupancy_grid(kernel, sk_warps(NT) * 32, smem, ntiles, nparts_cap, ln);
+        kernel<<<grid, sk_warps(NT) * 32, smem, ln.stream>>>(ly, cb, ntiles, esum_part);
         ln.tick();
         if (grid > *nparts) *nparts = grid;
     };

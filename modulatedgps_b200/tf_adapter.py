@@ -48,16 +48,19 @@ def _torch():
 # ---------------------------------------------------------------------------------------------------------------
 # tensor hand-off
 # ---------------------------------------------------------------------------------------------------------------
-def to_torch(t, device=None):
-    """TF tensor -> torch tensor through a DLPack capsule (no copy when it already lives on `device`)."""
+def to_torch(t, device=None, with_origin=False):
+    """TF tensor -> torch tensor through a DLPack capsule (no copy when it already lives on `device`).
+    with_origin=True also returns the device the TF tensor lived on, so that results can be handed back there."""
     torch = _torch()
     tf = _tf()
     x = torch.from_dlpack(tf.experimental.dlpack.to_dlpack(tf.convert_to_tensor(t)))
+    origin = x.device
     if x.dtype != torch.float64:
         x = x.to(torch.float64)
     if device is not None and x.device != device:
         x = x.to(device)
-    return x.contiguous()
+    x = x.contiguous()
+    return (x, origin) if with_origin else x
 
 
 def to_tf(x):
@@ -230,7 +233,8 @@ def build_training_loss(model, *, backend=None, noise: Optional[Callable] = None
     def eager_fwd_bwd(X, Y, *constrained):
         """EagerTensors in, [elbo] + gradients w.r.t. the constrained values (slot order) out."""
         dev = getattr(backend, "device", None)
-        vals = {name: to_torch(v, dev) for name, v in zip(slot_names, constrained)}
+        moved = {name: to_torch(v, dev, with_origin=True) for name, v in zip(slot_names, constrained)}
+        vals = {name: t for name, (t, _) in moved.items()}
         Xt, Yt = to_torch(X, dev), to_torch(Y, dev)
         pred = {k: vals[f"pred.{k}"] for k in LAYER_KEYS}
         assign = {k: vals[f"assign.{k}"] for k in LAYER_KEYS}
@@ -243,9 +247,9 @@ def build_training_loss(model, *, backend=None, noise: Optional[Callable] = None
                     vals.get("lik_var"), vals.get("assign_lik_var"), Xt, Yt, noise=nz,
                     seed=(int(seed) << 20) + state["calls"], point_offset=point_offset)
         backend.launch(m)
-        out = [to_tf(m.elbo.reshape(()))]
+        out = [to_tf(m.elbo.reshape(()).to(moved[slot_names[0]][1]))]
         for name, v in zip(slot_names, constrained):
-            g = m.grads[name]
+            g = m.grads[name].to(moved[name][1])       # a gradient goes back to the device its parameter came from
             shape = tuple(int(s) for s in v.shape)
             if g.numel() != _numel(shape):
                 g = g.sum().reshape(1)         # a scalar variance broadcast over the K components: sum of the parts

@@ -144,7 +144,8 @@ def workload_config(cfg, n_gpus):
     return {"workload": f"BASELINE config #{cfg.which}: synthetic N={cfg.N} (total), D={cfg.D}, M={cfg.M}, K={cfg.K}, "
                         f"S={cfg.S}, SMGP + GaussianModified, ELBO fwd+bwd step, Philox noise on device",
             "N": cfg.N, "D": cfg.D, "M": cfg.M, "K": cfg.K, "S": cfg.S, "points_per_gpu": cfg.N // n_gpus,
-            "sharding": f"dp{n_gpus}: contiguous row shards, parameters replicated, one all-reduce of the flat reduce buffer",
+            "sharding": f"dp{n_gpus}: contiguous row shards, parameters replicated, the flat reduce buffer all-reduced once "
+                        "per step (per layer, behind the C-ABI)",
             "l2": "no explicit flush: each step streams the materialised A (2 layers x M x N/gpus x 8 B = "
                   f"{2 * cfg.M * (cfg.N // n_gpus) * 8 / 1e9:.1f} GB) through HBM, far beyond the 126 MB L2"}
 
@@ -212,6 +213,9 @@ def main():
                          "configs[4] (#5: N=2^24, D=8, M=1024, K=8, S=32; meant for --gpus 8)")
     ap.add_argument("--points", type=int, default=None, help="total points (default: the configuration's own N)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="nccl", choices=["nccl", "torch"],
+                    help="N > 1: 'nccl' = ncclAllReduce issued by libmgp on a communicator attached to its context "
+                         "(mgp_ctx_set_comm); 'torch' = torch.distributed.all_reduce between the two C calls")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -251,7 +255,7 @@ def main():
     model = build_model(case)
     model.seed = 3
     if world > 1:
-        model.enable_data_parallel()
+        model.enable_data_parallel(collective=args.collective)
     ctx = _lib.get_context(dev)
     kw = dict(n_global=n_total, point_offset=rank * n_local)
 

@@ -28,6 +28,7 @@ extern "C" {
 #define MGP_ERR_CUDA 2
 #define MGP_ERR_NOT_PD 3   /* Cholesky of Kuu hit a non-positive pivot (TF: InvalidArgumentError) */
 #define MGP_ERR_NOMEM 4
+#define MGP_ERR_NCCL 6     /* a communicator is attached but NCCL failed or cannot be resolved */
 #define MGP_ERR_STALE_PRECOMPUTE 5   /* parameter values changed in place between mgp_elbo_local and mgp_elbo_finish */
 
 /* gpflow RobustMax.prob_is_largest squashes every Gaussian CDF into (s, 1 - s) before the product over classes:
@@ -103,6 +104,16 @@ int mgp_timing_enable(mgp_ctx* ctx, int on);
 int mgp_timing_read(mgp_ctx* ctx, double* ms, int64_t* calls, int reset);
 int mgp_num_stages(void);
 const char* mgp_stage_name(int i);
+/* Data parallelism without torch (mgp_ctx_create(device, nccl_comm_or_null, stream)): hand the
+ * context an initialised ncclComm_t (caller-owned; one rank per process; NULL detaches).  While one is attached,
+ * mgp_elbo_local leaves `reduce_buf` already summed over the ranks (ncclAllReduce, double, sum, on the context's stream:
+ * the header and the pred layer's part first, the assign layer's part behind it), so that
+ * mgp_elbo_local -> mgp_elbo_finish, and therefore mgp_elbo_fwd_bwd, are complete data-parallel steps: X / Y are this
+ * rank's shard, cfg.n_global the global batch size, noise->point_offset the shard's first global row.  NCCL is not
+ * linked: ncclAllReduce is looked up in the libnccl.so.2 already loaded in the process that created the communicator.
+ * mgp_all_reduce is the same collective on a caller buffer (e.g. for a caller that reduces its own statistics). */
+int mgp_ctx_set_comm(mgp_ctx* ctx, void* nccl_comm);
+int mgp_all_reduce(mgp_ctx* ctx, double* buf, int64_t n);
 /* Override MGP_ROBUSTMAX_CDF_SQUASH for this context (0 <= s < 0.5) — for the A/B replay of config #2 only. */
 int mgp_set_robustmax_squash(mgp_ctx* ctx, double squash);
 /* cap for the per-call point chunk (0 = automatic: whole shard if the materialised A fits the budget) */

@@ -13,7 +13,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmgp.so")
 
-MGP_OK, MGP_ERR_BAD_ARG, MGP_ERR_CUDA, MGP_ERR_NOT_PD, MGP_ERR_NOMEM, MGP_ERR_STALE_PRECOMPUTE = 0, 1, 2, 3, 4, 5
+(MGP_OK, MGP_ERR_BAD_ARG, MGP_ERR_CUDA, MGP_ERR_NOT_PD, MGP_ERR_NOMEM, MGP_ERR_STALE_PRECOMPUTE,
+ MGP_ERR_NCCL) = 0, 1, 2, 3, 4, 5, 6
 ROBUSTMAX_CDF_SQUASH = 1e-4      # MGP_ROBUSTMAX_CDF_SQUASH of include/mgp.h (tests/test_host_logic.py keeps them equal)
 MODEL_SMGP, MODEL_SMGP_MODIFIED = 0, 1
 LIK_GAUSSIAN, LIK_MULTICLASS = 0, 1
@@ -117,6 +118,8 @@ _PROTOTYPES = {
     "mgp_adam_step": (C.c_int, [C.c_void_p, C.POINTER(MgpAdamSlot), C.c_int32, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_double, C.c_int64, C.c_void_p]),
     "mgp_set_robustmax_squash": (C.c_int, [C.c_void_p, C.c_double]),
+    "mgp_ctx_set_comm": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mgp_all_reduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "mgp_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p,
                                   C.c_void_p]),
     "mgp_fill_triangular": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32]),
@@ -164,6 +167,7 @@ class Context:
             raise MgpError(rc, "mgp_ctx_create failed (no usable CUDA device?)")
         self.handle = h
         self.device = device
+        self.comm = None
 
     def check(self, rc: int):
         if rc == MGP_OK:
@@ -195,6 +199,11 @@ class Context:
 
     def set_robustmax_squash(self, squash: float):
         self.check(self.lib.mgp_set_robustmax_squash(self.handle, float(squash)))
+
+    def set_comm(self, nccl_comm):
+        """Attach (or, with None, detach) an ncclComm_t: mgp_elbo_local / mgp_elbo_fwd_bwd then all-reduce by themselves."""
+        self.check(self.lib.mgp_ctx_set_comm(self.handle, C.c_void_p(nccl_comm) if nccl_comm else None))
+        self.comm = nccl_comm
 
     def set_chunk_points(self, n: int):
         self.check(self.lib.mgp_set_chunk_points(self.handle, int(n)))

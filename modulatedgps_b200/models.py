@@ -260,14 +260,24 @@ class SMGP(SGP):
                 raise ValueError(f"layer has num_latent_gps={layer.num_latent_gps} but the model has K={K}")
 
     # -- data parallelism over the points -------------------------------------------
-    def enable_data_parallel(self, process_group=None):
-        """Each rank passes ITS shard of (X, Y) to the loss; per-shard sums are combined by one all-reduce of a
-        single flat buffer (NCCL over NVLink when the group's backend is nccl)."""
+    def enable_data_parallel(self, process_group=None, collective="torch"):
+        """Each rank passes ITS shard of (X, Y) to the loss; per-shard sums are combined by an all-reduce of the flat
+        reduce buffer (NCCL over NVLink when the group's backend is nccl).  collective = "torch": torch.distributed
+        reduces between mgp_elbo_local and mgp_elbo_finish; "nccl": a communicator of this model's own is attached to
+        the libmgp context (mgp_ctx_set_comm) and the C library issues ncclAllReduce itself — no torch.distributed call
+        on the step's path."""
         import torch.distributed as dist
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
+        if collective not in ("torch", "nccl"):
+            raise ValueError("collective must be 'torch' or 'nccl'")
         self.process_group = process_group
         self._dp = True
+        self._own_comm = None
+        if collective == "nccl":
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self._own_comm = parallel.create_nccl_comm(process_group, dev)
+            _lib.get_context(dev).set_comm(self._own_comm)
         return self
 
     # -- reference API ------------------------------------------------------------------------------
@@ -417,7 +427,7 @@ class SMGP(SGP):
         glik = torch.zeros(K, dtype=F64, device=dev)
         galik = torch.zeros(K, dtype=F64, device=dev)
         lib, h = ctx.lib, ctx.handle
-        if self._dp:
+        if self._dp and getattr(ctx, "comm", None) is None:
             rb = torch.empty(int(lib.mgp_reduce_buffer_len(C.byref(pv.struct), C.byref(av.struct))), dtype=F64, device=dev)
             ctx.check(lib.mgp_elbo_local(h, C.byref(cfg), C.byref(pv.struct), C.byref(av.struct), _lib.ptr(lik_var),
                                          _lib.ptr(alik_var), _lib.ptr(Xd), _lib.ptr(Yd), N, C.byref(nz), _lib.ptr(rb)))

@@ -74,10 +74,12 @@ class Cfg:
         nb64 = (Mp + 63) // 64
         syrk_pad = (64 * nb64 * (nb64 - 1) // 2 + 36 * nb64) / (M * (M + 1) / 2 / 64)
         unit = {"cond_fwd_a": 1, "cond_fwd_b": K, "syrk": K, "cond_bwd_a": K, "cond_bwd_b": 1}
+        unit["cond_fwd"] = 1 + K          # cond_fwd_a + cond_fwd_b in one kernel (32-point tiles)
         alg = {k: 2 * u * M * M for k, u in unit.items()}
         pad = {"cond_fwd_a": (nb + 1) / nb * (Mp / M) ** 2, "cond_fwd_b": (2 * nb + 1) / (2 * nb) * (Mp / M) ** 2,
                "syrk": syrk_pad, "cond_bwd_a": (2 * nb + 1) / (2 * nb) * (Mp / M) ** 2,
-               "cond_bwd_b": (2 * nb + 1) / (2 * nb) * (Mp / M) ** 2}
+               "cond_bwd_b": (2 * nb + 1) / (2 * nb) * (Mp / M) ** 2,
+               "cond_fwd": (2 * nb + 1) / (2 * nb) * (Mp / M) ** 2}
         return alg, {k: alg[k] * pad[k] for k in alg}
 
 

@@ -39,9 +39,9 @@ struct LayerSlot {
 }  // namespace
 
 enum Stage { ST_PRECOMPUTE = 0, ST_COND_FWD_A, ST_COND_FWD_B, ST_MC_PASS, ST_SYRK, ST_COND_BWD_A, ST_COND_BWD_B,
-             ST_REDUCE, ST_FINISH, ST_COUNT };
+             ST_REDUCE, ST_FINISH, ST_COND_FWD, ST_COUNT };
 static const char* const kStageNames[ST_COUNT] = {"precompute", "cond_fwd_a", "cond_fwd_b", "mc_pass", "syrk",
-                                                  "cond_bwd_a", "cond_bwd_b", "reduce_partials", "finish"};
+                                                  "cond_bwd_a", "cond_bwd_b", "reduce_partials", "finish", "cond_fwd"};
 
 // Optional per-stage device timing with CUDA events on the launch stream (bench.py's live roofline numbers).
 struct StageTimer {
@@ -446,8 +446,8 @@ int run_predict_f(mgp_ctx* c, LayerSlot& s, const double* X, int64_t N, double* 
     for (int64_t c0 = 0; c0 < N; c0 += Nc) {
         const int64_t n = (N - c0 < Nc) ? N - c0 : Nc;
         ChunkBuffers cb = chunk_of(s, X + c0 * D, n, ldn);
-        cond_fwd_a(s.dev, cb, ln);
-        cond_fwd_b(s.dev, cb, ln);
+        if (cond_fwd_is_fused(s.dev, cb)) cond_fwd_fused(s.dev, cb, ln);
+        else { cond_fwd_a(s.dev, cb, ln); cond_fwd_b(s.dev, cb, ln); }
         CUDA_TRY(c, cudaMemcpyAsync(fmean + c0 * K, cb.fmean, sizeof(double) * n * K, cudaMemcpyDeviceToDevice, c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(fvar + c0 * K, cb.fvar, sizeof(double) * n * K, cudaMemcpyDeviceToDevice, c->stream));
     }
@@ -883,10 +883,16 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
         const bool dual = !c->serial_layers && !c->timer.on;
         {
             const Launch la = dual ? fork_side(c) : ln;
-            { HostTimer ht("fwd_a p"); Timed t(c, ST_COND_FWD_A); cond_fwd_a(sp.dev, cp, ln); }
-            { HostTimer ht("fwd_b p"); Timed t(c, ST_COND_FWD_B); cond_fwd_b(sp.dev, cp, ln); }
-            { HostTimer ht("fwd_a a"); Timed t(c, ST_COND_FWD_A); cond_fwd_a(sa.dev, ca, la); }
-            { HostTimer ht("fwd_b a"); Timed t(c, ST_COND_FWD_B); cond_fwd_b(sa.dev, ca, la); }
+            if (cond_fwd_is_fused(sp.dev, cp)) { Timed t(c, ST_COND_FWD); cond_fwd_fused(sp.dev, cp, ln); }
+            else {
+                { HostTimer ht("fwd_a p"); Timed t(c, ST_COND_FWD_A); cond_fwd_a(sp.dev, cp, ln); }
+                { HostTimer ht("fwd_b p"); Timed t(c, ST_COND_FWD_B); cond_fwd_b(sp.dev, cp, ln); }
+            }
+            if (cond_fwd_is_fused(sa.dev, ca)) { Timed t(c, ST_COND_FWD); cond_fwd_fused(sa.dev, ca, la); }
+            else {
+                { HostTimer ht("fwd_a a"); Timed t(c, ST_COND_FWD_A); cond_fwd_a(sa.dev, ca, la); }
+                { HostTimer ht("fwd_b a"); Timed t(c, ST_COND_FWD_B); cond_fwd_b(sa.dev, ca, la); }
+            }
             if (dual) join_side(c);
         }
         McArgs m;

@@ -9,6 +9,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "exp_tab.h"
 #include "kernels.h"
 
 namespace mgp {
@@ -27,7 +28,8 @@ __global__ void prep_z_kernel(LayerDev ly) {
         double v = 0.0;
         if (i < M && d < D) v = ly.Z[(size_t)i * D + d] / ly.lengthscales[ly.n_ls == 1 ? 0 : d];  // Stationary.scale
         ly.Zs_rm[idx] = v;
-        ly.Zs_fm[wf_index(i, d, Dp)] = v;
+        // left operand of the Kuf exponent's contraction, in units of ln2/64 (stream_kernels.cu::exp2_tab)
+        ly.Zs_fm[wf_index(i, d, Dp)] = v * EXP_TAB_L;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < Mp; i += blockDim.x) {
@@ -37,11 +39,11 @@ __global__ void prep_z_kernel(LayerDev ly) {
             s += v * v;
         }
         ly.zs2[i] = s;
-        const double zh = log(ly.variance[0]) - 0.5 * s;
+        const double zh = (log(ly.variance[0]) - 0.5 * s) * EXP_TAB_L;
         ly.zh[i] = zh;
         if (D + 2 <= Dp) {   // kuf_fold (stream_kernels.cu): the exponent's row term rides in the padding columns of Zs_fm
             ly.Zs_fm[wf_index(i, D, Dp)] = i < M ? zh : 0.0;
-            ly.Zs_fm[wf_index(i, D + 1, Dp)] = i < M ? 1.0 : 0.0;
+            ly.Zs_fm[wf_index(i, D + 1, Dp)] = i < M ? EXP_TAB_L : 0.0;
         }
     }
 }

@@ -23,6 +23,7 @@
 // per point instead of once per (sample, point) (SGP.integrate only tiles X, models.py:35-36), and TF's
 // reverse pass through it (utils/training_utils.py:8-10).  Math: SURVEY.md Appendix B.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "exp_tab.h"
@@ -30,27 +31,31 @@
 
 namespace mgp {
 
-// exp(x) from a 64-entry table of 2^(j/64) and a degree-5 polynomial on |r| <= ln2/128: 10 FP64 instructions instead
-// of libdevice's 16-18, at most 1.03 ulp from expl (tools/exp_tab_check.c, tests/test_host_logic.py).  It matters out of proportion to its pipe time:
-// in the two-CTA kernels a scalar FP64 instruction waits behind the other CTA's 16-clock DMMAs (~30 clocks each,
-// measured), so the Kuf generation phase is as long as its FP64 instruction count.  `tab` is the shared-memory copy.
+// exp2_tab(y) = exp(y ln2 / 64) from a 64-entry table of 2^(j/64) and a degree-5 polynomial on |rr| <= 1/2 (rr in
+// units of ln2/64): 9 FP64 instructions instead of libdevice's 16-18 for exp, at most 1.1 ulp from expl
+// (tools/exp_tab_check.c, tests/test_host_logic.py).  The argument arrives ALREADY in units of ln2/64: the left operand
+// of the z.x contraction (Zs_fm, prep_z_kernel) is pre-scaled by 64/ln2, so the DMMA result needs no multiplication for
+// the range reduction, and k = round(y), rr = y - k are two exact additions.  Every scalar FP64 instruction here matters
+// out of proportion to its pipe time: measured in the fused forward kernel, a warp-wide scalar
+// FP64 instruction issued beside a saturated DMMA stream costs that sub-partition ~10 clocks, not 2.  The underflow test
+// runs on the integer pipe (sign-and-exponent word of y).  `tab` is the shared-memory copy of d_exp_tab64.
 __device__ const double d_exp_tab64[64] = {EXP_TAB64_VALUES};
-__device__ __forceinline__ double exp_tab(double x, const double* tab) {
+__device__ __forceinline__ double exp2_tab(double y, const double* tab) {
     const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: adding it rounds to the nearest integer in the low word
-    const double tt = fma(x, EXP_TAB_L, MAGIC);
+    const double tt = y + MAGIC;
     const int k = __double2loint(tt);
-    const double kf = tt - MAGIC;
-    double r = fma(kf, -EXP_TAB_C_HI, x);
-    r = fma(kf, -EXP_TAB_C_LO, r);
-    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p *= r;
+    const double rr = y - (tt - MAGIC);
+    double p = fma(rr, EXP2_C5, EXP2_C4);
+    p = fma(p, rr, EXP2_C3);
+    p = fma(p, rr, EXP2_C2);
+    p = fma(p, rr, EXP2_C1);
+    p *= rr;
     const double tj = tab[k & 63];
     const double res = fma(tj, p, tj);
     const double scaled = __hiloint2double(__double2hiint(res) + ((k >> 6) << 20), __double2loint(res));
-    return x < -700.0 ? 0.0 : scaled;   // (results below 1e-304 are flushed; the exponent add would leave the normal range)
+    // y < -700 * 64 / ln2 (results below 1e-304 are flushed; the exponent add would leave the normal range):
+    // for negative doubles the high word grows with the magnitude
+    return (unsigned)__double2hiint(y) > 0xC0EF8F17u ? 0.0 : scaled;
 }
 
 // DMMA consumer warps per CTA: 8 with 32-point tiles (two warps per SM sub-partition keep the pipe ~90 % busy when a
@@ -63,6 +68,8 @@ constexpr int SK_CTHREADS = SK_WARPS * 32;
 __host__ __device__ constexpr int sk_warps(int nt) { return nt == 32 ? SK_WARPS : SK_WARPS_NT16; }
 
 __host__ __device__ inline int xs_stride(int Dp) { return ((Dp - 4 + 15) / 16) * 16 + 4; }
+// 8-wide feature blocks of the kernel-gradient sums: features {1, xs_d, xs_d^2}, 1 + 2 D of them
+__host__ __device__ inline int esum_feature_blocks(int D) { return (1 + 2 * D + 7) / 8; }
 
 // 16-row block dealt to warp w in round r (snake order); returns -1 past the end
 template <int NW = SK_WARPS>
@@ -229,8 +236,8 @@ struct WPair {
 // returns the whole exponent: two FP64 additions per Kuf element less on the pipe the kernel is bound by.
 __host__ __device__ inline bool kuf_fold(int D, int Dp) { return D + 2 <= Dp; }
 
-// Xs[n][d] = X[n0+n][d] / lengthscale_d (0 outside the chunk / padding); xs2[n] = -|Xs_n|^2 / 2 (column term of the
-// Kuf exponent).  One warp.
+// Xs[n][d] = X[n0+n][d] / lengthscale_d (0 outside the chunk / padding); xs2[n] = -|Xs_n|^2 / 2 * 64/ln2 (column term of
+// the Kuf exponent for the path without free padding columns, in exp2_tab's units).  One warp.
 template <int NT>
 __device__ __forceinline__ void stage_x_warp(const LayerDev& ly, const ChunkBuffers& cb, int64_t n0, double* Xs,
                                              double* xs2, int lane) {
@@ -246,7 +253,7 @@ __device__ __forceinline__ void stage_x_warp(const LayerDev& ly, const ChunkBuff
     for (int n = lane; n < NT; n += 32) {
         double s = 0.0;
         for (int d = 0; d < D; ++d) s += Xs[n * XSTR + d] * Xs[n * XSTR + d];
-        xs2[n] = -0.5 * s;
+        xs2[n] = -0.5 * s * EXP_TAB_L;   // (units of ln2/64, like the contraction's result: see exp2_tab)
         if (fold) {   // the two free padding columns of the contraction carry the row and column terms of the exponent
             Xs[n * XSTR + D] = 1.0;
             Xs[n * XSTR + D + 1] = -0.5 * s;
@@ -279,7 +286,7 @@ __device__ __forceinline__ void gen_kuf_block(const LayerDev& ly, int rb8, const
 #pragma unroll
         for (int nf = 0; nf < NF; ++nf)
 #pragma unroll
-            for (int e = 0; e < 2; ++e) kv[nf][e] = live ? exp_tab(kv[nf][e], etab) : 0.0;
+            for (int e = 0; e < 2; ++e) kv[nf][e] = live ? exp2_tab(kv[nf][e], etab) : 0.0;
         return;
     }
     const double zh = __ldg(ly.zh + i);
@@ -288,7 +295,7 @@ __device__ __forceinline__ void gen_kuf_block(const LayerDev& ly, int rb8, const
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const double arg = kv[nf][e] + (zh + xs2[nf * 8 + 2 * t + e]);
-            kv[nf][e] = live ? exp_tab(arg, etab) : 0.0;
+            kv[nf][e] = live ? exp2_tab(arg, etab) : 0.0;
         }
 }
 
@@ -515,6 +522,206 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + 32, 1) cond_fwd_b_kernel(L
 }
 
 // ==================================================================================================
+// cond_fwd_fused (32-point tiles, M <= ~300):  cond_fwd_a and cond_fwd_b in ONE persistent kernel.
+//   generator warps (4)   Kuf tile of point tile i + 1 -> buffer G  (z.x contraction on DMMA + table exp), while
+//   consumer warps (8)    phase 1: A = L^-1 G  -> buffer Abuf (+ global A, for SYRK and the backward)
+//                         phase 2: K passes B_k = Lq_k^T Abuf -> global B_k, partial column norms / q_mu^T A
+//   warp 8 (a generator)  also finishes fmean / fvar of the previous tile.
+// Why: stand-alone, cond_fwd_a has only M^2 of DMMA per tile to hide its scalar-FP64 generation phase behind (three
+// barrier-phased CTAs per SM, DMMA pipe 72 %); here the generation runs on its own warps under (1 + K) M^2 of DMMA and
+// the L^-1 product runs at the rate of the other passes.  The A tile never travels HBM -> SM for the B_k passes, and
+// one launch (fill + tail) per layer disappears.
+// Hand-offs per tile (mbarriers, phase = tile parity):   g_full  G written (4 generator warps)
+//   g_free  consumers done reading G (8)        a_ready  Abuf written (8)
+//   a_free  consumers done reading Abuf + finisher done with |a|^2 (9)        p_done  partial sums written (8)
+// A consumer computes the L^-1 product of the NEXT tile's first row block before it waits for a_free, so the skew
+// between warps at the tile boundary is absorbed by work.
+// ==================================================================================================
+constexpr int FU_GEN_WARPS = 4;
+template <int NT>
+__global__ void __launch_bounds__((SK_WARPS + FU_GEN_WARPS) * 32, 1) cond_fwd_fused_kernel(LayerDev ly, ChunkBuffers cb, int ntiles, int dbg) {
+    constexpr int NF = NT / 8, STR = NT + 4, NW = SK_WARPS;
+    extern __shared__ __align__(16) double smem[];
+    const int Mp = ly.Mp, K = ly.K, XSTR = xs_stride(ly.Dp);
+    uint64_t* g_full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* g_free = g_full + 1;
+    uint64_t* a_ready = g_full + 2;
+    uint64_t* a_free = g_full + 3;
+    uint64_t* p_done = g_full + 4;
+    const size_t tile_elems = (size_t)Mp * STR;
+    double* G = smem + SK_BAR_DOUBLES;                          // [Mp][STR]  Kuf tile
+    double* Abuf = G + tile_elems;                              // [Mp][STR]  A tile
+    double* sqpart = Abuf + tile_elems;                         // [2][NW][K][NT]  partial sum_m B_k^2 (by tile parity)
+    double* mnpart = sqpart + (size_t)2 * NW * K * NT;          // [2][NW][K][NT]  partial q_mu^T A
+    double* Xsb = mnpart + (size_t)2 * NW * K * NT;             // [2]{[NT][XSTR], [NT]} scaled X rows (by tile parity)
+    const int xs_elems = NT * XSTR + NT;
+    __shared__ double etab[64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int nb16 = Mp / 16, nb8 = Mp / 8, C4 = Mp / 4;
+    if (threadIdx.x < 64) etab[threadIdx.x] = d_exp_tab64[threadIdx.x];
+    if (threadIdx.x == 0) {
+        mbar_init(g_full, FU_GEN_WARPS); mbar_init(g_free, NW); mbar_init(a_ready, NW); mbar_init(a_free, NW + 1);
+        mbar_init(p_done, NW);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto tile_of = [&](int i) { return (int64_t)blockIdx.x + (int64_t)i * gridDim.x; };
+
+    if (warp >= NW) {   // ---- generators (+ finisher = warp NW) ----
+        const int gw = warp - NW;
+        const double variance = ly.variance[0];
+        auto finish = [&](int i) {   // warp NW: fmean / fvar of tile i
+            const int64_t n0 = tile_of(i) * NT;
+            const unsigned ph = (unsigned)(i & 1);
+            mbar_wait(a_ready, ph);
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int m = 0; m < Mp; m += 4) {
+                const double v0 = Abuf[(size_t)m * STR + lane], v1 = Abuf[(size_t)(m + 1) * STR + lane];
+                const double v2 = Abuf[(size_t)(m + 2) * STR + lane], v3 = Abuf[(size_t)(m + 3) * STR + lane];
+                s0 = fma(v0, v0, s0); s1 = fma(v1, v1, s1); s2 = fma(v2, v2, s2); s3 = fma(v3, v3, s3);
+            }
+            const double asq = (s0 + s1) + (s2 + s3);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_free);
+            mbar_wait(p_done, ph);
+            const double* sq = sqpart + (size_t)(i & 1) * NW * K * NT;
+            const double* mn = mnpart + (size_t)(i & 1) * NW * K * NT;
+            for (int k = 0; k < K; ++k) {
+                double sv = 0.0, mv = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    sv += sq[((size_t)w * K + k) * NT + lane];
+                    mv += mn[((size_t)w * K + k) * NT + lane];
+                }
+                cb.fvar[(size_t)(n0 + lane) * K + k] = (variance - asq) + sv;   // Knn - sum A^2 + sum LTA^2
+                cb.fmean[(size_t)(n0 + lane) * K + k] = mv;
+            }
+        };
+        for (int i = 0; i < my_tiles; ++i) {
+            double* Xs = Xsb + (size_t)(i & 1) * xs_elems;
+            double* xs2 = Xs + NT * XSTR;
+            if (gw == 0) stage_x_warp<NT>(ly, cb, tile_of(i) * NT, Xs, xs2, lane);
+            named_bar_sync(2, FU_GEN_WARPS * 32);                           // X rows visible to the four generator warps
+            if (i > 0) mbar_wait(g_free, (unsigned)((i - 1) & 1));          // consumers have left G
+            for (int rb = gw; rb < nb8; rb += FU_GEN_WARPS) {
+                double kv[NF][2];
+                if (dbg & 1) {   // timing experiment only: no generation arithmetic
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf) kv[nf][0] = kv[nf][1] = 1e-3;
+                } else {
+                    gen_kuf_block<NT>(ly, rb, Xs, xs2, etab, kv, lane);
+                }
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf)
+                    *reinterpret_cast<double2*>(G + (size_t)(rb * 8 + g) * STR + nf * 8 + 2 * t) = make_double2(kv[nf][0], kv[nf][1]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(g_full);
+            if (gw == 0 && i > 0) finish(i - 1);
+        }
+        if (gw == 0 && my_tiles > 0) finish(my_tiles - 1);
+        return;
+    }
+
+    // ---- consumers ----
+    const int nmy = my_block_count<NW>(warp, nb16);
+    const int mkb0 = warp * (C4 / NW), mkb1 = mkb0 + C4 / NW;   // this warp's k-slice of the fmean contraction
+    auto seg_a = [&](int r) { const int b = snake_block<NW>(r, warp, nb16); return Seg{ly.W_Linv, 2 * b, 0}; };
+    auto seg_b = [&](int k, int r) {
+        const int b = snake_block<NW>(r, warp, nb16);
+        return Seg{ly.W_LqT + (size_t)k * Mp * Mp, 2 * b, 4 * b};
+    };
+    WPair wp;
+    if (nmy > 0) wfrag_load(wp.f, seg_a(0), C4, 0, lane);
+    for (int i = 0; i < my_tiles; ++i) {
+        const int64_t tile = tile_of(i);
+        const unsigned ph = (unsigned)(i & 1);
+        double* Aout = cb.A + (size_t)tile * tile_elems;
+        double* sq = sqpart + ((size_t)(i & 1) * NW + warp) * K * NT;
+        double* mn = mnpart + ((size_t)(i & 1) * NW + warp) * K * NT;
+        // ---- phase 1: rows of A = L^-1 G (lower triangular) ----
+        mbar_wait(g_full, ph);
+        for (int r = 0; r < nmy; ++r) {
+            const int b = snake_block<NW>(r, warp, nb16);
+            double acc[2][NF][2];
+            zero_acc<NF>(acc);
+            const Seg nxt = (r + 1 < nmy) ? seg_a(r + 1) : seg_b(0, 0);
+            wp.template run<NT, TRI_LOWER>(seg_a(r), (b + 1) * 4, C4, G, acc, lane, nxt);
+            if (r == 0 && i > 0) mbar_wait(a_free, (unsigned)((i - 1) & 1));   // Abuf of the previous tile is no longer read
+#pragma unroll
+            for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) {
+                    const size_t off = (size_t)(b * 16 + mf * 8 + g) * STR + nf * 8 + 2 * t;
+                    const double2 v = make_double2(acc[mf][nf][0], acc[mf][nf][1]);
+                    *reinterpret_cast<double2*>(Abuf + off) = v;
+                    if (!(dbg & 2)) *reinterpret_cast<double2*>(Aout + off) = v;
+                }
+        }
+        if (nmy == 0 && i > 0) mbar_wait(a_free, (unsigned)((i - 1) & 1));
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(g_free); mbar_arrive(a_ready); }
+        mbar_wait(a_ready, ph);
+        // ---- phase 2: B_k = Lq_k^T A (upper triangular), partial norms and means ----
+        const double* T = Abuf;
+        for (int k = 0; k < K; ++k) {
+            double colsq[NF][2];
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf) colsq[nf][0] = colsq[nf][1] = 0.0;
+            double* Bk = cb.Bk ? cb.Bk + ((size_t)k * cb.tiles_cap + tile) * tile_elems : nullptr;
+            for (int r = 0; r < nmy; ++r) {
+                const int b = snake_block<NW>(r, warp, nb16);
+                double acc[2][NF][2];
+                zero_acc<NF>(acc);
+                const Seg nxt = (r + 1 < nmy) ? seg_b(k, r + 1) : (k + 1 < K ? seg_b(k + 1, 0) : seg_a(0));
+                wp.template run<NT, TRI_UPPER>(seg_b(k, r), C4, C4, T, acc, lane, nxt);
+#pragma unroll
+                for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf) {
+                        if (Bk)
+                            *reinterpret_cast<double2*>(Bk + (size_t)(b * 16 + mf * 8 + g) * STR + nf * 8 + 2 * t) =
+                                make_double2(acc[mf][nf][0], acc[mf][nf][1]);
+                        colsq[nf][0] = fma(acc[mf][nf][0], acc[mf][nf][0], colsq[nf][0]);
+                        colsq[nf][1] = fma(acc[mf][nf][1], acc[mf][nf][1], colsq[nf][1]);
+                    }
+            }
+            double v[8];
+#pragma unroll
+            for (int nf = 0; nf < 4; ++nf) { v[2 * nf] = colsq[nf < NF ? nf : 0][0]; v[2 * nf + 1] = colsq[nf < NF ? nf : 0][1]; }
+            sq[(size_t)k * NT + (g >> 1) * 8 + 2 * t + (g & 1)] = reduce8_over_g(v, lane);
+        }
+        {   // this warp's slice of fmean^T [K x NT] = q_mu^T [K x Mp] * A tile (rows >= K of W_mT are zero)
+            double acc[2][NF][2];
+            zero_acc<NF>(acc);
+            const double* wm = ly.W_mT + (size_t)mkb0 * 32 + lane;
+            const double* tb = T + t * STR + g;
+            for (int kb = mkb0; kb < mkb1; kb += 2) {
+                const double a0 = __ldg(wm + (size_t)(kb - mkb0) * 32);
+                const double* tr0 = tb + (size_t)kb * 4 * STR;
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) dmma(acc[0][nf], a0, tr0[nf * 8]);
+                if (kb + 1 < mkb1) {
+                    const double a1 = __ldg(wm + (size_t)(kb + 1 - mkb0) * 32);
+                    const double* tr1 = tb + (size_t)(kb + 1) * 4 * STR;
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf) dmma(acc[1][nf], a1, tr1[nf * 8]);
+                }
+            }
+            if (g < K) {
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf)
+                    *reinterpret_cast<double2*>(mn + (size_t)g * NT + nf * 8 + 2 * t) =
+                        make_double2(acc[0][nf][0] + acc[1][nf][0], acc[0][nf][1] + acc[1][nf][1]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(a_free); mbar_arrive(p_done); }
+    }
+}
+
+// ==================================================================================================
 // cond_bwd_a  (triangular route)
 //   Abar = sum_k Lq_k * (B_k diag(2 vbar_k))  +  q_mu * mubar^T  -  2 A diag(sum_k vbar_k)
 // from fvar = variance - |a|^2 + sum |b_k|^2, b_k = Lq_k^T a, fmean = a^T q_mu.  The right operand changes with k:
@@ -720,8 +927,9 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_bwd_b_kernel(LayerDev 
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // Abar tile landed (bulk copy) AND X rows staged: 2 arrivals
     uint64_t* tfree = full + 1;                            // every warp has finished multiplying from T: 8 arrivals
     double* T = smem + SK_BAR_DOUBLES;
-    double* Xsb = T + (size_t)Mp * STR;                    // [2]{[NT][XSTR], [NT]} scaled X rows, by tile parity
-    const int xs_elems = NT * XSTR + NT;
+    double* Xsb = T + (size_t)Mp * STR;                    // [2]{[NT][XSTR], [NT], [NT][FS]} scaled X rows / features, by tile parity
+    const int FB = esum_feature_blocks(D), FS = 8 * FB + 2;   // feature row stride == 2 mod 8: conflict-free B fragments
+    const int xs_elems = NT * XSTR + NT + NT * FS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const int nb16 = Mp / 16, C4 = Mp / 4;
     const size_t tile_elems = (size_t)Mp * STR;
@@ -745,6 +953,17 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_bwd_b_kernel(LayerDev 
     auto stage_x = [&](int tile, int it) {   // warp 1
         double* Xs = Xsb + (size_t)(it & 1) * xs_elems;
         stage_x_warp<NT>(ly, cb, (int64_t)tile * NT, Xs, Xs + NT * XSTR, lane);
+        // features of the E-sums, Phi[n][f] = {1, xs_d, xs_d^2}: right operand of the small DMMA product below
+        double* Ph = Xs + NT * XSTR + NT;
+        for (int idx = lane; idx < NT * 8 * FB; idx += 32) {
+            const int n = idx / (8 * FB), f = idx % (8 * FB);
+            double v = 0.0;
+            if (f == 0) v = 1.0;
+            else if (f <= D) v = Xs[n * XSTR + f - 1];
+            else if (f <= 2 * D) { const double x = Xs[n * XSTR + f - 1 - D]; v = x * x; }
+            Ph[n * FS + f] = v;
+        }
+        __syncwarp();
         if (lane == 0) mbar_arrive(full);
     };
     if ((int)blockIdx.x < ntiles) {
@@ -765,39 +984,33 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_bwd_b_kernel(LayerDev 
             zero_acc<NF>(acc);
             wgemm_seg<NT, TRI_UPPER>(seg_of(i), C4, C4, T, acc, lane, wf, seg_of(i + 1 < nmy ? i + 1 : 0));   // upper triangular
             if (i == nmy - 1) { __syncwarp(); if (lane == 0) mbar_arrive(tfree); }   // this warp is done with T
+            const double* Ph = xs2 + NT;
 #pragma unroll
             for (int mf = 0; mf < 2; ++mf) {
                 double kv[NF][2];
                 gen_kuf_block<NT>(ly, 2 * b + mf, Xs, xs2, etab, kv, lane);
-                double e0 = 0.0;
 #pragma unroll
                 for (int nf = 0; nf < NF; ++nf)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        acc[mf][nf][e] *= kv[nf][e];   // E = Kuf_bar .* Kuf
-                        e0 += acc[mf][nf][e];
-                    }
+                    for (int e = 0; e < 2; ++e) acc[mf][nf][e] *= kv[nf][e];   // E = Kuf_bar .* Kuf
+                // sum_n E[i][n] Phi[n][f] on DMMA: the C fragment of E is read as A fragments over the point subsets
+                // {nf*8 + 2t + e : t = 0..3}, the matching rows of Phi as B fragments.  (Per element this replaces 2 + 3 D
+                // scalar FP64 instructions, each of which costs the tensor pipe several DMMA issue slots, by 1/4 DMMA.)
                 double* p = my_part + (size_t)(b * 16 + mf * 8 + g) * E;
-                // fire-and-forget reductions: each address has exactly ONE writer (this lane, this CTA's private slot), so
-                // the accumulation order is fixed and the result deterministic; RED avoids the load-add-store round trip
-                e0 = sum_over_t(e0);
-                if (t == 0) atomicAdd(p, e0);
-                for (int d = 0; d < D; ++d) {
-                    double e1 = 0.0, e2 = 0.0;
+                for (int fb = 0; fb < FB; ++fb) {
+                    double R[2] = {0.0, 0.0};
 #pragma unroll
                     for (int nf = 0; nf < NF; ++nf)
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const double x = Xs[(nf * 8 + 2 * t + e) * XSTR + d];
-                            const double ex = acc[mf][nf][e] * x;
-                            e1 += ex;
-                            e2 += ex * x;
-                        }
-                    e1 = sum_over_t(e1);
-                    e2 = sum_over_t(e2);
-                    if (t == 0) {
-                        atomicAdd(p + 1 + d, e1);
-                        atomicAdd(p + 1 + Dp + d, e2);
+                        for (int e = 0; e < 2; ++e) dmma(R, acc[mf][nf][e], Ph[(nf * 8 + 2 * t + e) * FS + fb * 8 + g]);
+                    // fire-and-forget reductions: each address has exactly ONE writer (this lane, this CTA's private slot),
+                    // so the accumulation order is fixed and the result deterministic
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int f = fb * 8 + 2 * t + j;
+                        if (f == 0) atomicAdd(p, R[j]);
+                        else if (f <= D) atomicAdd(p + f, R[j]);
+                        else if (f <= 2 * D) atomicAdd(p + 1 + Dp + (f - 1 - D), R[j]);
                     }
                 }
             }
@@ -825,7 +1038,7 @@ static size_t extras_bytes(int Mp, int Dp, int K, int nt, int nbuf = 2) {
     const size_t fa = (size_t)(nt * xs_stride(Dp) + nt) * 8;
     const size_t fb = (size_t)nbuf * (sk_warps(nt) + SK_WARPS) * K * nt * 8;
     const size_t ba = (size_t)4 * nt * KP * 8;
-    const size_t bb = (size_t)2 * (nt * xs_stride(Dp) + nt) * 8;
+    const size_t bb = (size_t)2 * (nt * xs_stride(Dp) + nt + nt * (8 * ((1 + 2 * Dp + 7) / 8) + 2)) * 8;
     size_t m = fa;
     if (fb > m) m = fb;
     if (ba > m) m = ba;
@@ -877,6 +1090,28 @@ void cond_fwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
     if (NT == 32) launch(cond_fwd_a_kernel<32>); else launch(cond_fwd_a_kernel<16>);
 }
 
+// bytes of dynamic shared memory of the fused forward kernel, or 0 when the layer does not qualify (32-point tiles only)
+static size_t fused_fwd_smem(const LayerDev& ly, int NT) {
+    // OFF by default: measured SLOWER than the two kernels (23.7 vs 23.1 ms at config #4) — the Kuf
+    // generation's scalar FP64 instructions cost the consumers' DMMA stream ~1.5 ms wherever they run
+    if (NT != 32 || getenv("MGP_FUSED_FWD") == nullptr) return 0;
+    const size_t bytes = ((size_t)SK_BAR_DOUBLES + (size_t)2 * ly.Mp * (NT + 4) + (size_t)4 * SK_WARPS * ly.K * NT +
+                          (size_t)2 * (NT * xs_stride(ly.Dp) + NT)) * sizeof(double);
+    return bytes <= (size_t)227 * 1024 - 1024 ? bytes : 0;
+}
+bool cond_fwd_is_fused(const LayerDev& ly, const ChunkBuffers& cb) { return fused_fwd_smem(ly, cb.tw) != 0; }
+
+void cond_fwd_fused(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
+    const int NT = cb.tw;
+    const size_t smem = fused_fwd_smem(ly, NT);
+    const int threads = (SK_WARPS + FU_GEN_WARPS) * 32;
+    const int ntiles = (int)((cb.n + NT - 1) / NT);
+    const int grid = persistent_grid(cond_fwd_fused_kernel<32>, threads, smem, ntiles, 0, ln);
+    static const int dbg = getenv("MGP_FUSED_DBG") ? atoi(getenv("MGP_FUSED_DBG")) : 0;
+    cond_fwd_fused_kernel<32><<<grid, threads, smem, ln.stream>>>(ly, cb, ntiles, dbg);
+    ln.tick();
+}
+
 void cond_fwd_b(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
     const int NT = cb.tw, nbuf = ring_depth(ly.Mp, ly.Dp, ly.K, NT);
     const int threads = sk_warps(NT) * 32 + 32;
@@ -919,7 +1154,8 @@ void cond_bwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
 void cond_bwd_b(const LayerDev& ly, const ChunkBuffers& cb, double* esum_part, int nparts_cap, int* nparts,
                 const Launch& ln) {
     const int NT = cb.tw;
-    const size_t smem = ((size_t)SK_BAR_DOUBLES + (size_t)ly.Mp * (NT + 4) + 2 * (NT * xs_stride(ly.Dp) + NT)) * sizeof(double);
+    const size_t smem = ((size_t)SK_BAR_DOUBLES + (size_t)ly.Mp * (NT + 4) +
+                         2 * (NT * xs_stride(ly.Dp) + NT + NT * (8 * esum_feature_blocks(ly.D) + 2))) * sizeof(double);
     const int ntiles = (int)((cb.n + NT - 1) / NT);
     auto launch = [&](auto kernel) {
         const int grid = occupancy_grid(kernel, sk_warps(NT) * 32, smem, ntiles, nparts_cap, ln);

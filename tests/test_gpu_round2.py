@@ -473,3 +473,35 @@ def test_training_trajectory_matches_the_oracle(name, steps, hg):
     for key, p in dev_params.items():
         ref = cons(key).detach().numpy()
         assert relerr(np.asarray(p.value().detach().cpu()).reshape(ref.shape), ref) <= 1e-6, key
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the fused forward kernel (kept selectable: measured slower than cond_fwd_a + cond_fwd_b)
+# ---------------------------------------------------------------------------------------------------------------
+def test_fused_forward_kernel_matches_the_goldens(hg, monkeypatch):
+    """MGP_FUSED_FWD=1 routes 32-point-tile layers through cond_fwd_fused (generator warps + L^-1 product + K passes in
+    one persistent kernel); results must be the two-kernel path's."""
+    from modulatedgps_b200 import _lib
+    from oracle import svgp_mixture as O
+    ctx = _lib.get_context()
+    monkeypatch.setenv("MGP_FUSED_FWD", "1")
+    for name in ("demo_tf2.pert", "synth4_small.pert", "shape_d5_k1.pert", "demo_john_doe_fullbatch.pert"):
+        case, g = load_golden(name)
+        model = hg.build_model(case)
+        elbo, grads = model.elbo_and_grads(g["X"], g["Y"], noise=(g["z"], g["u"]))
+        assert abs(float(elbo) - float(g["out.elbo"])) <= RTOL * abs(float(g["out.elbo"])), name
+        for k in ("pred.Z", "pred.q_sqrt", "assign.q_mu", "assign.lengthscales"):
+            r = g["out.grad." + k]
+            assert relerr(grads[k].cpu().numpy().reshape(r.shape), r) <= RTOL, (name, k)
+        fm, fv = model.pred_layer.predict_f(g["Xtest"])
+        assert relerr(np.asarray(fm), g["out.predict_f.pred.mean"]) <= RTOL and relerr(np.asarray(fv), g["out.predict_f.pred.var"]) <= RTOL
+    case, X, Y, z, u = _case(3000, 2, 256, 4, 16, seed=3000)
+    model = hg.build_model(case)
+    e1, g1 = model.elbo_and_grads(X, Y, noise=(z, u))
+    g1 = {k: v.clone() for k, v in g1.items()}
+    monkeypatch.delenv("MGP_FUSED_FWD")
+    e0, g0 = model.elbo_and_grads(X, Y, noise=(z, u))
+    ctx.check_status()
+    assert abs(float(e1) - float(e0)) <= 1e-12 * abs(float(e0))
+    for k in g0:
+        assert relerr(g1[k].cpu().numpy(), g0[k].cpu().numpy()) <= 1e-10, k

@@ -19,3 +19,8 @@ print(", \\\n".join("    " + ", ".join(repr(x) for x in tab[i:i + 4]) for i in r
 print(f"#define EXP_TAB_L {64.0 / math.log(2.0)!r}       /* 64 / ln 2 */")
 print(f"#define EXP_TAB_C_HI {hi!r}   /* ln 2 / 64, top 32 bits */")
 print(f"#define EXP_TAB_C_LO {lo!r}   /* remainder */")
+# exp2_tab(): argument already in units of ln2/64 (y = x * 64 / ln 2, produced by the z.x contraction itself):
+# 2^(rr/64) - 1 = sum_i EXP2_C_i rr^i, EXP2_C_i = (ln2/64)^i / i!, |rr| <= 1/2
+for i in range(1, 6):
+    ci = (ln2 / 64) ** i / Decimal(math.factorial(i))
+    print(f"#define EXP2_C{i} {float(ci)!r}")

@@ -28,7 +28,7 @@ struct Buf {
 struct LayerSlot {
     LayerDev dev{};
     Buf inv_ls, Zs_rm, Zs_fm, zs2, zh, Kuu, L, Linv, Dinv, W_Linv, W_LinvT, Lq_rm, W_LqT, Q_rm, W_Lq, W_m, W_mT, T1, T2, T3, Sfull, rowout;
-    Buf A, Bk, fmean, fvar, mubar, vbar;   // chunk buffers
+    Buf A, Bk, Kuf, fmean, fvar, mubar, vbar;   // chunk buffers
     Buf syrk_part, mraw_part, esum_part;    // per-CTA partial sums
     Buf syrk_plan;                          // SyrkWork[] of the current (Mp, K, chunk length)
     int64_t plan_key[3] = {-1, -1, -1};
@@ -260,6 +260,13 @@ int setup_layer(mgp_ctx* c, LayerSlot& s, const mgp_layer* l, bool need_bwd) {
     return MGP_OK;
 }
 
+// cond_fwd_a keeps the Kuf tiles it generates (one more tile-major array of A's size per layer) so that cond_bwd_b
+// multiplies by them instead of generating them again; MGP_NO_KUF_STASH=1 restores the regeneration (A/B timing)
+static bool kuf_stash_enabled() {
+    static const bool on = getenv("MGP_NO_KUF_STASH") == nullptr;
+    return on;
+}
+
 int ensure_chunk(mgp_ctx* c, LayerSlot& s, int64_t ldn, bool need_bwd) {
     const size_t Mp = s.dev.Mp, K = s.dev.K;
     const size_t tw = layer_tile_width(s.dev.Mp, s.dev.Dp, s.dev.K);
@@ -269,6 +276,7 @@ int ensure_chunk(mgp_ctx* c, LayerSlot& s, int64_t ldn, bool need_bwd) {
     TRY(ensure(c, s.fvar, (size_t)ldn * K * 8, true));
     if (need_bwd) {
         TRY(ensure(c, s.Bk, K * tiled, true));
+        if (kuf_stash_enabled()) TRY(ensure(c, s.Kuf, tiled, true));
         TRY(ensure(c, s.mubar, (size_t)ldn * K * 8, true));
         TRY(ensure(c, s.vbar, (size_t)ldn * K * 8, true));
     }
@@ -294,7 +302,7 @@ ChunkBuffers chunk_of(const LayerSlot& s, const double* X, int64_t n, int64_t ld
     cb.n = n; cb.ldn = ldn; cb.X = X;
     cb.tw = layer_tile_width(s.dev.Mp, s.dev.Dp, s.dev.K);
     cb.tiles_cap = ldn / cb.tw;
-    cb.A = (double*)s.A.p; cb.Bk = nullptr; cb.fmean = (double*)s.fmean.p; cb.fvar = (double*)s.fvar.p;
+    cb.A = (double*)s.A.p; cb.Bk = nullptr; cb.Kuf = nullptr; cb.fmean = (double*)s.fmean.p; cb.fvar = (double*)s.fvar.p;
     cb.mubar = (double*)s.mubar.p; cb.vbar = (double*)s.vbar.p;
     return cb;
 }
@@ -360,7 +368,7 @@ int64_t pick_chunk_uncached(mgp_ctx* c, int64_t N, int Mp_max, int nlayers, int 
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         double budget = fmin(0.4 * (double)c->total_mem, 0.7 * (double)free_b);
-        for (int i = 0; i < 2; ++i) budget += (double)c->slot[i].A.cap + (double)c->slot[i].Bk.cap;   // what we already hold counts as available
+        for (int i = 0; i < 2; ++i) budget += (double)c->slot[i].A.cap + (double)c->slot[i].Bk.cap + (double)c->slot[i].Kuf.cap;   // what we already hold counts as available
         cap = (int64_t)(budget / ((double)nlayers * ((1.0 + kcopies) * Mp_max + 6 * MGP_MAX_K) * 8.0));
         if (cap < 4096) cap = 4096;
     }
@@ -499,7 +507,7 @@ void mgp_ctx_destroy(mgp_ctx* c) {
     auto rel = [](Buf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; };
     for (auto& s : c->slot) {
         Buf* all[] = {&s.inv_ls, &s.Zs_rm, &s.Zs_fm, &s.zs2, &s.zh, &s.Kuu, &s.L, &s.Linv, &s.Dinv, &s.W_Linv, &s.W_LinvT, &s.Lq_rm,
-                      &s.W_LqT, &s.Q_rm, &s.W_Lq, &s.W_m, &s.W_mT, &s.T1, &s.T2, &s.T3, &s.Sfull, &s.rowout, &s.A, &s.Bk,
+                      &s.W_LqT, &s.Q_rm, &s.W_Lq, &s.W_m, &s.W_mT, &s.T1, &s.T2, &s.T3, &s.Sfull, &s.rowout, &s.A, &s.Bk, &s.Kuf,
                       &s.fmean, &s.fvar, &s.mubar, &s.vbar, &s.syrk_part, &s.mraw_part, &s.esum_part,
                       &s.syrk_plan};
         for (Buf* b : all) rel(*b);
@@ -861,7 +869,7 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
 
     const int Mp_max = sp.dev.Mp > sa.dev.Mp ? sp.dev.Mp : sa.dev.Mp;
     int64_t Nc;
-    { HostTimer ht("pick_chunk (cudaMemGetInfo)"); Nc = pick_chunk(c, N_local, Mp_max, 2, K); }
+    { HostTimer ht("pick_chunk (cudaMemGetInfo)"); Nc = pick_chunk(c, N_local, Mp_max, 2, K + (kuf_stash_enabled() ? 1 : 0)); }
     const int64_t ldn = round_up64(Nc, 64);
     HostTimer ht_rest("elbo_local after pick_chunk");
     TRY(ensure_chunk(c, sp, ldn, true));
@@ -875,6 +883,10 @@ int mgp_elbo_local(mgp_ctx* c, const mgp_elbo_cfg* cfg, const mgp_layer* pred, c
         ChunkBuffers cp = chunk_of(sp, X + c0 * D, n, ldn), ca = chunk_of(sa, X + c0 * D, n, ldn);
         cp.Bk = (double*)sp.Bk.p;
         ca.Bk = (double*)sa.Bk.p;
+        if (kuf_stash_enabled()) {   // (the fused forward kernel does not keep its Kuf tiles)
+            if (!cond_fwd_is_fused(sp.dev, cp)) cp.Kuf = (double*)sp.Kuf.p;
+            if (!cond_fwd_is_fused(sa.dev, ca)) ca.Kuf = (double*)sa.Kuf.p;
+        }
         // The two layers are independent until the Monte-Carlo pass and again after it: the assign layer's streaming
         // kernels go to the side stream, so that its CTAs fill the SMs the pred layer's persistent CTAs leave at their
         // tail (and the other way round) instead of every launch paying its own fill and tail — a per-launch loss of

@@ -117,6 +117,21 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
+// shared -> global bulk copy of this thread's bulk-async group (the shared-memory source must have been made visible to
+// the async proxy: writers execute fence_proxy_async() before the barrier that precedes the copy)
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+// the issuing thread's bulk stores have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// pull `bytes` (multiple of 16) at a 16-byte aligned global address into L2
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // deterministic block-wide sum of one double per thread; result valid in thread 0.  `red` >= 32 doubles.
 __device__ __forceinline__ double block_sum(double v, double* red) {
     v = warp_sum(v);

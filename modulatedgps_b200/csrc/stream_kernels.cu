@@ -343,7 +343,11 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_fwd_a_kernel(LayerDev 
             for (int nf = 0; nf < NF; ++nf)
                 *reinterpret_cast<double2*>(T + (size_t)(rb * 8 + g) * STR + nf * 8 + 2 * t) = make_double2(kv[nf][0], kv[nf][1]);
         }
+        // The generated tile is kept for cond_bwd_b (E = Kuf_bar .* Kuf) instead of being generated a second time there:
+        // ONE bulk store of the shared-memory image by one thread, read by the async proxy while the warps multiply.
+        if (cb.Kuf) fence_proxy_async();
         __syncthreads();
+        if (cb.Kuf && threadIdx.x == 0) bulk_s2g(cb.Kuf + (size_t)tile * tile_elems, T, (unsigned)(tile_elems * sizeof(double)));
         for (int i = 0; i < nmy; ++i) {
             const int b = snake_block<NW>(i, warp, nb16);
             double acc[2][NF][2];
@@ -357,6 +361,7 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_fwd_a_kernel(LayerDev 
                     *reinterpret_cast<double2*>(Aout + (size_t)(b * 16 + mf * 8 + g) * STR + nf * 8 + 2 * t) =
                         make_double2(acc[mf][nf][0], acc[mf][nf][1]);
         }
+        if (cb.Kuf && threadIdx.x == 0) bulk_wait_read();   // T is overwritten after the barrier
         __syncthreads();
     }
 }
@@ -920,7 +925,7 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
 // ==================================================================================================
 template <int NT>
 __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_bwd_b_kernel(LayerDev ly, ChunkBuffers cb, int ntiles,
-                                                                      double* esum_part) {
+                                                                      double* esum_part, int pf_next) {
     constexpr int NF = NT / 8, STR = NT + 4, NW = sk_warps(NT);
     extern __shared__ __align__(16) double smem[];
     const int Mp = ly.Mp, Dp = ly.Dp, D = ly.D, XSTR = xs_stride(Dp), E = 1 + 2 * Dp;
@@ -949,6 +954,11 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_bwd_b_kernel(LayerDev 
     auto load_tile = [&](int tile) {   // thread 0
         mbar_arrive_expect_tx(full, tile_bytes);
         bulk_g2s(T, cb.A + (size_t)tile * tile_elems, tile_bytes, full);
+        // the Kuf tile cond_fwd_a kept: on its way into L2 while the warps multiply; the epilogues read it from there
+        if (cb.Kuf) bulk_prefetch_l2(cb.Kuf + (size_t)tile * tile_elems, tile_bytes);
+        // T is single-buffered (two CTAs per SM), so the NEXT Abar tile can only be copied once every warp has left the
+        // multiply phase: have it waiting in L2 by then instead of in HBM
+        if (pf_next && tile + (int)gridDim.x < ntiles) bulk_prefetch_l2(cb.A + (size_t)(tile + gridDim.x) * tile_elems, tile_bytes);
     };
     auto stage_x = [&](int tile, int it) {   // warp 1
         double* Xs = Xsb + (size_t)(it & 1) * xs_elems;
@@ -988,7 +998,16 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_bwd_b_kernel(LayerDev 
 #pragma unroll
             for (int mf = 0; mf < 2; ++mf) {
                 double kv[NF][2];
-                gen_kuf_block<NT>(ly, 2 * b + mf, Xs, xs2, etab, kv, lane);
+                if (cb.Kuf) {   // (CTA-uniform) the values cond_fwd_a generated, in C-fragment order
+                    const double* kt = cb.Kuf + (size_t)tile * tile_elems + (size_t)((2 * b + mf) * 8 + g) * STR + 2 * t;
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf) {
+                        const double2 q = __ldcs(reinterpret_cast<const double2*>(kt + nf * 8));
+                        kv[nf][0] = q.x; kv[nf][1] = q.y;
+                    }
+                } else {
+                    gen_kuf_block<NT>(ly, 2 * b + mf, Xs, xs2, etab, kv, lane);
+                }
 #pragma unroll
                 for (int nf = 0; nf < NF; ++nf)
 #pragma unroll
@@ -1159,7 +1178,8 @@ void cond_bwd_b(const LayerDev& ly, const ChunkBuffers& cb, double* esum_part, i
     const int ntiles = (int)((cb.n + NT - 1) / NT);
     auto launch = [&](auto kernel) {
         const int grid = occupancy_grid(kernel, sk_warps(NT) * 32, smem, ntiles, nparts_cap, ln);
-        kernel<<<grid, sk_warps(NT) * 32, smem, ln.stream>>>(ly, cb, ntiles, esum_part);
+        static const int pf_next = getenv("MGP_BWD_B_NO_PF") ? 0 : 1;   // (A/B timing switch)
+        kernel<<<grid, sk_warps(NT) * 32, smem, ln.stream>>>(ly, cb, ntiles, esum_part, pf_next);
         ln.tick();
         if (grid > *nparts) *nparts = grid;
     };

@@ -262,10 +262,7 @@ int setup_layer(mgp_ctx* c, LayerSlot& s, const mgp_layer* l, bool need_bwd) {
 
 // cond_fwd_a keeps the Kuf tiles it generates (one more tile-major array of A's size per layer) so that cond_bwd_b
 // multiplies by them instead of generating them again; MGP_NO_KUF_STASH=1 restores the regeneration (A/B timing)
-static bool kuf_stash_enabled() {
-    static const bool on = getenv("MGP_NO_KUF_STASH") == nullptr;
-    return on;
-}
+static bool kuf_stash_enabled() { return getenv("MGP_NO_KUF_STASH") == nullptr; }   // (read per call: tests toggle it)
 
 int ensure_chunk(mgp_ctx* c, LayerSlot& s, int64_t ldn, bool need_bwd) {
     const size_t Mp = s.dev.Mp, K = s.dev.K;

@@ -267,16 +267,21 @@ __device__ __forceinline__ void stage_x_warp(const LayerDev& ly, const ChunkBuff
 // exp(zs.xs + (log variance - |zs|^2/2) + (-|xs|^2/2)): the same cancellation as the reference's r2, two FP64
 // instructions instead of four around the exponential.  The zs.xs contraction runs on DMMA (north_star:
 // "squared-distance term on FP64 DMMA").  `etab`: shared-memory copy of d_exp_tab64.
+// `zs`: the fragment-major scaled inducing inputs — ly.Zs_fm, or a shared-memory copy of it (the generation is a latency
+// chain load -> DMMA -> exp -> store per 8-row block; with the copy its first link is a 30-clock LDS, not an L2 access).
 template <int NT>
 __device__ __forceinline__ void gen_kuf_block(const LayerDev& ly, int rb8, const double* Xs, const double* xs2,
-                                              const double* etab, double (&kv)[NT / 8][2], int lane) {
+                                              const double* etab, double (&kv)[NT / 8][2], int lane,
+                                              const double* zs = nullptr, bool have_z0 = false, double z0 = 0.0) {
     constexpr int NF = NT / 8;
     const int g = lane >> 2, t = lane & 3;
     const int Dp = ly.Dp, XSTR = xs_stride(Dp), D4 = Dp >> 2;
 #pragma unroll
     for (int nf = 0; nf < NF; ++nf) kv[nf][0] = kv[nf][1] = 0.0;
     for (int kd = 0; kd < D4; ++kd) {
-        const double a = __ldg(ly.Zs_fm + ((size_t)rb8 * D4 + kd) * 32 + lane);
+        // (have_z0: the caller already holds k4-block 0 of this row block's Z fragments)
+        const double a = (have_z0 && kd == 0) ? z0
+                         : zs ? zs[((size_t)rb8 * D4 + kd) * 32 + lane] : __ldg(ly.Zs_fm + ((size_t)rb8 * D4 + kd) * 32 + lane);
 #pragma unroll
         for (int nf = 0; nf < NF; ++nf) dmma(kv[nf], a, Xs[(nf * 8 + g) * XSTR + kd * 4 + t]);
     }
@@ -314,7 +319,7 @@ constexpr int SK_BAR_DOUBLES = 8;   // room for 2 x NBUF mbarriers (NBUF <= 2) +
 // (measured: 9.1 ms vs 6.2 ms for this form at config #4).
 // ==================================================================================================
 template <int NT>
-__global__ void __launch_bounds__(sk_warps(NT) * 32) cond_fwd_a_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
+__global__ void __launch_bounds__(sk_warps(NT) * 32, NT == 32 ? 3 : 1) cond_fwd_a_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
     constexpr int NF = NT / 8, STR = NT + 4, NW = sk_warps(NT);
     extern __shared__ __align__(16) double smem[];
     const int Mp = ly.Mp, XSTR = xs_stride(ly.Dp);
@@ -335,8 +340,27 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_fwd_a_kernel(LayerDev 
         const int64_t n0 = (int64_t)tile * NT;
         double* Aout = cb.A + (size_t)tile * tile_elems;
         if (warp == 0) stage_x_warp<NT>(ly, cb, n0, Xs, xs2, lane);
+        // the first Z fragment of each 8-row block this warp generates, requested BEFORE the barrier: the generation is a
+        // latency chain (L2 load -> DMMA -> exp -> store) per block, and this takes its first link out of the chain
+        constexpr int ZQ = 6;   // blocks warp, warp + NW, ... (Mp <= 352 at 32-point tiles: at most 6 per warp)
+        double z0[ZQ];
+#pragma unroll
+        for (int q = 0; q < ZQ; ++q) {
+            const int rb = warp + q * NW;
+            z0[q] = rb < nb8 ? __ldg(ly.Zs_fm + (size_t)rb * (ly.Dp >> 2) * 32 + lane) : 0.0;
+        }
         __syncthreads();
-        for (int rb = warp; rb < nb8; rb += NW) {
+#pragma unroll
+        for (int q = 0; q < ZQ; ++q) {
+            const int rb = warp + q * NW;
+            if (rb >= nb8) break;
+            double kv[NF][2];
+            gen_kuf_block<NT>(ly, rb, Xs, xs2, etab, kv, lane, nullptr, true, z0[q]);
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf)
+                *reinterpret_cast<double2*>(T + (size_t)(rb * 8 + g) * STR + nf * 8 + 2 * t) = make_double2(kv[nf][0], kv[nf][1]);
+        }
+        for (int rb = warp + ZQ * NW; rb < nb8; rb += NW) {   // (larger M: 16-point tiles)
             double kv[NF][2];
             gen_kuf_block<NT>(ly, rb, Xs, xs2, etab, kv, lane);
 #pragma unroll
@@ -362,6 +386,98 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_fwd_a_kernel(LayerDev 
                         make_double2(acc[mf][nf][0], acc[mf][nf][1]);
         }
         if (cb.Kuf && threadIdx.x == 0) bulk_wait_read();   // T is overwritten after the barrier
+        __syncthreads();
+    }
+}
+
+// ==================================================================================================
+// cond_fwd_a, software-pipelined form (32-point tiles, two tile buffers):  ONE persistent CTA per SM.
+// The barrier-phased form above leaves the DMMA pipe idle 22 % of the time (ncu: stall_barrier 4.4 per issue): its three
+// CTAs per SM fall into step — they share the pipe, so CTAs that multiply together finish together and then generate
+// together.  Here every warp generates ITS rows of tile i + 1 (into the other buffer) between the row blocks of tile i
+// it multiplies, so a warp's generation phase (a latency-bound chain: L2 load -> 4 DMMA -> table exp -> store) always
+// runs beside the other warp of its sub-partition multiplying; a dedicated generator-warp ring starved (DESIGN.md
+// section 5), warps that alternate cannot.  One CTA-wide barrier per tile; warp 8 stages the X rows two tiles ahead.
+// ==================================================================================================
+template <int NT>
+__global__ void __launch_bounds__(SK_WARPS * 32 + 32, 1) cond_fwd_a_pipe_kernel(LayerDev ly, ChunkBuffers cb, int ntiles,
+                                                                               int zs_in_smem) {
+    constexpr int NF = NT / 8, STR = NT + 4, NW = SK_WARPS;
+    extern __shared__ __align__(16) double smem[];
+    const int Mp = ly.Mp, XSTR = xs_stride(ly.Dp);
+    const size_t tile_elems = (size_t)Mp * STR;
+    double* Tb = smem;                                   // [2][Mp][STR]
+    double* Xsb = Tb + 2 * tile_elems;                   // [2]{[NT][XSTR], [NT]}
+    const int xs_elems = NT * XSTR + NT;
+    double* zsm = Xsb + 2 * xs_elems;                    // [Mp * Dp] copy of Zs_fm (zs_in_smem)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int nb16 = Mp / 16, nb8 = Mp / 8, C4 = Mp / 4;
+    __shared__ double etab[64];
+    if (threadIdx.x < 64) etab[threadIdx.x] = d_exp_tab64[threadIdx.x];
+    if (zs_in_smem)
+        for (int i = threadIdx.x; i < Mp * ly.Dp; i += blockDim.x) zsm[i] = ly.Zs_fm[i];
+    const double* zs = zs_in_smem ? zsm : nullptr;
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto tile_of = [&](int i) { return (int64_t)blockIdx.x + (int64_t)i * gridDim.x; };
+    auto stage = [&](int i) {   // warp NW: scaled X rows of this CTA's i-th tile
+        double* Xs = Xsb + (size_t)(i & 1) * xs_elems;
+        stage_x_warp<NT>(ly, cb, tile_of(i) * NT, Xs, Xs + NT * XSTR, lane);
+    };
+    // rows [8 rb, 8 rb + 8) of the Kuf tile i -> buffer i & 1
+    auto gen = [&](int i, int rb) {
+        const double* Xs = Xsb + (size_t)(i & 1) * xs_elems;
+        double* T = Tb + (size_t)(i & 1) * tile_elems;
+        double kv[NF][2];
+        gen_kuf_block<NT>(ly, rb, Xs, Xs + NT * XSTR, etab, kv, lane, zs);
+#pragma unroll
+        for (int nf = 0; nf < NF; ++nf)
+            *reinterpret_cast<double2*>(T + (size_t)(rb * 8 + g) * STR + nf * 8 + 2 * t) = make_double2(kv[nf][0], kv[nf][1]);
+    };
+    const int ngen = warp < NW ? (nb8 - warp + NW - 1) / NW : 0;   // 8-row blocks warp, warp + NW, ... of every tile
+    if (warp == NW && my_tiles > 0) stage(0);
+    __syncthreads();
+    if (my_tiles > 0) {
+        if (warp == NW) { if (my_tiles > 1) stage(1); }
+        else for (int q = 0; q < ngen; ++q) gen(0, warp + q * NW);
+    }
+    if (cb.Kuf) fence_proxy_async();
+    __syncthreads();
+
+    const int nmy = warp < NW ? my_block_count<NW>(warp, nb16) : 0;
+    auto seg_of = [&](int i) { const int b = snake_block<NW>(i, warp, nb16); return Seg{ly.W_Linv, 2 * b, 0}; };
+    WFrag wf;
+    if (nmy > 0) wfrag_load(wf, seg_of(0), C4, 0, lane);
+    for (int i = 0; i < my_tiles; ++i) {
+        const int64_t tile = tile_of(i);
+        const double* T = Tb + (size_t)(i & 1) * tile_elems;
+        const bool more = i + 1 < my_tiles;
+        if (warp == NW) {
+            // kept for cond_bwd_b: one bulk store of the finished Kuf tile (its writers fenced before the last barrier)
+            if (cb.Kuf && lane == 0) bulk_s2g(cb.Kuf + (size_t)tile * tile_elems, T, (unsigned)(tile_elems * sizeof(double)));
+            if (i + 2 < my_tiles) stage(i + 2);     // buffer i & 1 of the X rows: tile i's generation ended before the last barrier
+            if (cb.Kuf && lane == 0) bulk_wait_read();   // buffer i & 1 of T is generated into again after the next barrier
+        } else {
+            double* Aout = cb.A + (size_t)tile * tile_elems;
+            int q = 0;
+            for (int r = 0; r < nmy; ++r) {
+                const int b = snake_block<NW>(r, warp, nb16);
+                double acc[2][NF][2];
+                zero_acc<NF>(acc);
+                wgemm_seg<NT>(seg_of(r), (b + 1) * 4, C4, T, acc, lane, wf, seg_of(r + 1 < nmy ? r + 1 : 0));   // lower triangular
+#pragma unroll
+                for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf)
+                        *reinterpret_cast<double2*>(Aout + (size_t)(b * 16 + mf * 8 + g) * STR + nf * 8 + 2 * t) =
+                            make_double2(acc[mf][nf][0], acc[mf][nf][1]);
+                if (more) {   // this warp's share of the next tile's generation, spread over its row blocks
+                    const int q1 = (r + 1) * ngen / nmy;
+                    for (; q < q1; ++q) gen(i + 1, warp + q * NW);
+                }
+            }
+            if (more) for (; q < ngen; ++q) gen(i + 1, warp + q * NW);
+            if (cb.Kuf) fence_proxy_async();
+        }
         __syncthreads();
     }
 }
@@ -1046,6 +1162,115 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_bwd_b_kernel(LayerDev 
 }
 
 // ==================================================================================================
+// cond_bwd_b, ring form (32-point tiles, Kuf tiles kept by cond_fwd_a):  ONE persistent CTA per SM like cond_fwd_b.
+// With the Kuf values read back instead of generated, the per-block epilogue is 8 loads (issued BEFORE the block's
+// multiply: a one-CTA kernel has the registers), 16 multiplications, 16 DMMAs and 4 reductions — no exponentials, no
+// dependent scalar chain — so the kernel no longer needs a second CTA to hide it, and the single-buffered tile of the
+// two-CTA form (next copy only after every warp has left the multiply phase) becomes a two-deep ring fed by warp 8,
+// which also stages the X rows / E-sum features of the tile.
+// ==================================================================================================
+template <int NT, int NBUF>
+__global__ void __launch_bounds__(SK_WARPS * 32 + 32, 1) cond_bwd_b_ring_kernel(LayerDev ly, ChunkBuffers cb, int ntiles,
+                                                                              double* esum_part) {
+    constexpr int NF = NT / 8, STR = NT + 4, NW = SK_WARPS;
+    extern __shared__ __align__(16) double smem[];
+    const int Mp = ly.Mp, Dp = ly.Dp, D = ly.D, XSTR = xs_stride(Dp), E = 1 + 2 * Dp;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);   // Abar tile landed and X rows / features staged
+    uint64_t* done = full + NBUF;                          // every consumer warp has finished the tile
+    double* Tb = smem + SK_BAR_DOUBLES;                    // [NBUF][Mp][STR]
+    const size_t tile_elems = (size_t)Mp * STR;
+    double* Xsb = Tb + (size_t)NBUF * tile_elems;          // [NBUF]{[NT][XSTR], [NT], [NT][FS]}
+    const int FB = esum_feature_blocks(D), FS = 8 * FB + 2;
+    const int xs_elems = NT * XSTR + NT + NT * FS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int nb16 = Mp / 16, C4 = Mp / 4;
+    const unsigned tile_bytes = (unsigned)(tile_elems * sizeof(double));
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], NW); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto tile_of = [&](int i) { return (int64_t)blockIdx.x + (int64_t)i * gridDim.x; };
+
+    if (warp == NW) {   // ---- producer: X rows, features, Abar tile ----
+        for (int i = 0; i < my_tiles; ++i) {
+            const int buf = i % NBUF;
+            const int64_t tile = tile_of(i);
+            if (i >= NBUF) mbar_wait(&done[buf], (unsigned)(((i / NBUF) - 1) & 1));
+            double* Xs = Xsb + (size_t)buf * xs_elems;
+            stage_x_warp<NT>(ly, cb, tile * NT, Xs, Xs + NT * XSTR, lane);
+            double* Ph = Xs + NT * XSTR + NT;   // Phi[n][f] = {1, xs_d, xs_d^2}: right operand of the E-sum product
+            for (int idx = lane; idx < NT * 8 * FB; idx += 32) {
+                const int n = idx / (8 * FB), f = idx % (8 * FB);
+                double v = 0.0;
+                if (f == 0) v = 1.0;
+                else if (f <= D) v = Xs[n * XSTR + f - 1];
+                else if (f <= 2 * D) { const double x = Xs[n * XSTR + f - 1 - D]; v = x * x; }
+                Ph[n * FS + f] = v;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                bulk_prefetch_l2(cb.Kuf + (size_t)tile * tile_elems, tile_bytes);
+                mbar_arrive_expect_tx(&full[buf], tile_bytes);
+                bulk_g2s(Tb + (size_t)buf * tile_elems, cb.A + (size_t)tile * tile_elems, tile_bytes, &full[buf]);
+            }
+        }
+        return;
+    }
+    // ---- consumers ----
+    double* my_part = esum_part + (size_t)blockIdx.x * Mp * E;
+    const int nmy = my_block_count<NW>(warp, nb16);
+    auto seg_of = [&](int i) { const int b = snake_block<NW>(i, warp, nb16); return Seg{ly.W_LinvT, 2 * b, 4 * b}; };
+    WFrag wf;
+    if (nmy > 0) wfrag_load(wf, seg_of(0), C4, seg_of(0).kb0, lane);
+    for (int i = 0; i < my_tiles; ++i) {
+        const int buf = i % NBUF;
+        const double* T = Tb + (size_t)buf * tile_elems;
+        const double* Ph = Xsb + (size_t)buf * xs_elems + NT * XSTR + NT;
+        const double* ktile = cb.Kuf + (size_t)tile_of(i) * tile_elems;
+        mbar_wait(&full[buf], (unsigned)((i / NBUF) & 1));
+        for (int r = 0; r < nmy; ++r) {
+            const int b = snake_block<NW>(r, warp, nb16);
+            // the block's Kuf values (C-fragment order), in flight while the block is multiplied
+            double2 kq[2][NF];
+#pragma unroll
+            for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf)
+                    kq[mf][nf] = __ldcs(reinterpret_cast<const double2*>(ktile + (size_t)((2 * b + mf) * 8 + g) * STR + nf * 8 + 2 * t));
+            double acc[2][NF][2];
+            zero_acc<NF>(acc);
+            wgemm_seg<NT, TRI_UPPER>(seg_of(r), C4, C4, T, acc, lane, wf, seg_of(r + 1 < nmy ? r + 1 : 0));   // upper triangular
+#pragma unroll
+            for (int mf = 0; mf < 2; ++mf) {
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) { acc[mf][nf][0] *= kq[mf][nf].x; acc[mf][nf][1] *= kq[mf][nf].y; }   // E = Kuf_bar .* Kuf
+                double* p = my_part + (size_t)(b * 16 + mf * 8 + g) * E;
+                for (int fb = 0; fb < FB; ++fb) {   // sum_n E[i][n] Phi[n][f] on DMMA (see cond_bwd_b_kernel), two chains
+                    double R0[2] = {0.0, 0.0}, R1[2] = {0.0, 0.0};
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf) {
+                        dmma(R0, acc[mf][nf][0], Ph[(nf * 8 + 2 * t) * FS + fb * 8 + g]);
+                        dmma(R1, acc[mf][nf][1], Ph[(nf * 8 + 2 * t + 1) * FS + fb * 8 + g]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {   // one writer per address (this lane, this CTA's slot): deterministic
+                        const int f = fb * 8 + 2 * t + j;
+                        const double v = R0[j] + R1[j];
+                        if (f == 0) atomicAdd(p, v);
+                        else if (f <= D) atomicAdd(p + f, v);
+                        else if (f <= 2 * D) atomicAdd(p + 1 + Dp + (f - 1 - D), v);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&done[buf]);
+    }
+}
+
+// ==================================================================================================
 // host side
 // ==================================================================================================
 int stream_max_parts(const Launch& ln) { return ln.num_sms * 4; }
@@ -1067,6 +1292,7 @@ static size_t extras_bytes(int Mp, int Dp, int K, int nt, int nbuf = 2) {
 }
 int layer_tile_width(int Mp, int Dp, int K) {
     const size_t cap = 227 * 1024;
+    if (getenv("MGP_TILE_W16")) return 16;   // (timing experiment: 16-point tiles / 16 consumer warps at any M)
     return (2 * (size_t)Mp * 36 * 8 + extras_bytes(Mp, Dp, K, 32) <= cap) ? 32 : 16;
 }
 static int ring_depth(int Mp, int Dp, int K, int nt) {
@@ -1101,6 +1327,19 @@ void cond_fwd_a(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
     const size_t smem = ((size_t)ly.Mp * (NT + 4) + NT * xs_stride(ly.Dp) + NT) * sizeof(double);
     const int ntiles = (int)((cb.n + NT - 1) / NT);
     const int threads = sk_warps(NT) * 32;
+    // measured at config #4: software-pipelined form 5.94 ms (6.14 before its Z fragments moved to shared memory), the
+    // barrier-phased form with three CTAs per SM 5.43 ms -> the pipelined form stays selectable only
+    const bool pipe = getenv("MGP_FWD_A_PIPE") != nullptr;   // (A/B timing switch; tests cover both forms)
+    if (NT == 32 && pipe) {   // software-pipelined form: one CTA per SM, two tile buffers (they fit whenever NT = 32)
+        size_t psmem = ((size_t)2 * ly.Mp * (NT + 4) + 2 * (NT * xs_stride(ly.Dp) + NT)) * sizeof(double);
+        const size_t zbytes = (size_t)ly.Mp * ly.Dp * sizeof(double);
+        const int zs_in_smem = psmem + zbytes <= (size_t)226 * 1024;
+        if (zs_in_smem) psmem += zbytes;
+        const int grid = persistent_grid(cond_fwd_a_pipe_kernel<32>, SK_CTHREADS + 32, psmem, ntiles, 0, ln);
+        cond_fwd_a_pipe_kernel<32><<<grid, SK_CTHREADS + 32, psmem, ln.stream>>>(ly, cb, ntiles, zs_in_smem);
+        ln.tick();
+        return;
+    }
     auto launch = [&](auto kernel) {
         const int grid = occupancy_grid(kernel, threads, smem, ntiles, 0, ln);
         kernel<<<grid, threads, smem, ln.stream>>>(ly, cb, ntiles);
@@ -1176,9 +1415,20 @@ void cond_bwd_b(const LayerDev& ly, const ChunkBuffers& cb, double* esum_part, i
     const size_t smem = ((size_t)SK_BAR_DOUBLES + (size_t)ly.Mp * (NT + 4) +
                          2 * (NT * xs_stride(ly.Dp) + NT + NT * (8 * esum_feature_blocks(ly.D) + 2))) * sizeof(double);
     const int ntiles = (int)((cb.n + NT - 1) / NT);
+    // measured at config #4: ring form 5.47 ms, two CTAs per SM 5.28 ms -> the ring form stays selectable only
+    const bool ring = getenv("MGP_BWD_B_RING") != nullptr;   // (A/B timing switch; tests cover both forms)
+    if (NT == 32 && cb.Kuf && ring) {   // ring form: one CTA per SM, two-deep tile ring
+        const size_t rsmem = ((size_t)SK_BAR_DOUBLES + (size_t)2 * ly.Mp * (NT + 4) +
+                              2 * (NT * xs_stride(ly.Dp) + NT + NT * (8 * esum_feature_blocks(ly.D) + 2))) * sizeof(double);
+        const int grid = persistent_grid(cond_bwd_b_ring_kernel<32, 2>, SK_CTHREADS + 32, rsmem, ntiles, nparts_cap, ln);
+        cond_bwd_b_ring_kernel<32, 2><<<grid, SK_CTHREADS + 32, rsmem, ln.stream>>>(ly, cb, ntiles, esum_part);
+        ln.tick();
+        if (grid > *nparts) *nparts = grid;
+        return;
+    }
     auto launch = [&](auto kernel) {
         const int grid = occupancy_grid(kernel, sk_warps(NT) * 32, smem, ntiles, nparts_cap, ln);
-        static const int pf_next = getenv("MGP_BWD_B_NO_PF") ? 0 : 1;   // (A/B timing switch)
+        const int pf_next = getenv("MGP_BWD_B_NO_PF") ? 0 : 1;   // (A/B timing switch)
         kernel<<<grid, sk_warps(NT) * 32, smem, ln.stream>>>(ly, cb, ntiles, esum_part, pf_next);
         ln.tick();
         if (grid > *nparts) *nparts = grid;

@@ -505,3 +505,32 @@ def test_fused_forward_kernel_matches_the_goldens(hg, monkeypatch):
     assert abs(float(e1) - float(e0)) <= 1e-12 * abs(float(e0))
     for k in g0:
         assert relerr(g1[k].cpu().numpy(), g0[k].cpu().numpy()) <= 1e-10, k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the alternative forms of cond_fwd_a / cond_bwd_b (selectable for A/B timing) compute the same numbers
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("env", [{"MGP_NO_KUF_STASH": "1"}, {"MGP_FWD_A_PIPE": "1", "MGP_BWD_B_RING": "1"},
+                                 {"MGP_FWD_A_PIPE": "1", "MGP_NO_KUF_STASH": "1"}])
+def test_alternative_kernel_forms_agree(hg, monkeypatch, env):
+    """Default: barrier-phased cond_fwd_a that keeps its Kuf tiles, two-CTA cond_bwd_b that reads them back.
+    MGP_FWD_A_PIPE / MGP_BWD_B_RING select the one-CTA software-pipelined / ring forms (measured slower),
+    MGP_NO_KUF_STASH makes cond_bwd_b generate Kuf again.  The Kuf values are bit-identical either way; only the order
+    of the E-sum accumulation differs."""
+    from modulatedgps_b200 import _lib
+    ctx = _lib.get_context()
+    cases = [_case(3000, 2, 256, 4, 16, seed=3000), _case(700, 5, 96, 3, 8, seed=7), _case(1500, 3, 400, 2, 4, seed=11)]
+    for case, X, Y, z, u in cases:
+        model = hg.build_model(case)
+        e0, g0 = model.elbo_and_grads(X, Y, noise=(z, u))
+        g0 = {k: v.clone() for k, v in g0.items()}
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        e1, g1 = model.elbo_and_grads(X, Y, noise=(z, u))
+        g1 = {k: v.clone() for k, v in g1.items()}
+        for k in env:
+            monkeypatch.delenv(k)
+        ctx.check_status()
+        assert abs(float(e1) - float(e0)) <= 1e-12 * abs(float(e0))
+        for k in g0:
+            assert relerr(g1[k].cpu().numpy(), g0[k].cpu().numpy()) <= 1e-10, k

@@ -846,8 +846,12 @@ __global__ void __launch_bounds__((SK_WARPS + FU_GEN_WARPS) * 32, 1) cond_fwd_fu
 // cond_bwd_a  (triangular route)
 //   Abar = sum_k Lq_k * (B_k diag(2 vbar_k))  +  q_mu * mubar^T  -  2 A diag(sum_k vbar_k)
 // from fvar = variance - |a|^2 + sum |b_k|^2, b_k = Lq_k^T a, fmean = a^T q_mu.  The right operand changes with k:
-// per point tile the ring carries K + 1 stages (B_0 .. B_{K-1}, then A for the elementwise epilogue); each warp keeps
-// the accumulators of ALL its row blocks (NBW of them) in registers across the stages of a tile.
+// per point tile the ring carries K stages (B_0 .. B_{K-1}); each warp keeps the accumulators of ALL its row blocks
+// (NBW of them) in registers across the stages of a tile.  The A tile of the elementwise epilogue is NOT a ring stage:
+// it used to be a (K + 1)-th, very short one, and in a two-deep ring the stage after a short stage has only that
+// stage's duration to land (B_0 of the next tile: ~1.5 k clocks for a 74 KB copy, ~4 k clocks exposed per tile).  The
+// tile is pulled into L2 when the tile's first stage is issued, and each lane reads the 16 bytes it overwrites
+// straight from there in the epilogue that follows the last stage.
 // PROD_WARP: warp 8 feeds the ring; otherwise (accumulators too large for the 168-register cap of a 9-warp CTA: three
 // warps on one SM sub-partition) the last warp to leave a stage refills its buffer (shared-memory arrival counter).
 // ==================================================================================================
@@ -875,19 +879,19 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
     }
     __syncthreads();
     const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int total = my_tiles * (K + 1);
+    const int total = my_tiles * K;
     auto tile_of = [&](int ti) { return (int64_t)blockIdx.x + (int64_t)ti * gridDim.x; };
-    // stage j = (tile iteration ti, s): s < K -> B_s tile, s == K -> A tile.  One lane issues.
+    // stage j = (tile iteration ti, s): the B_s tile.  One lane issues.
     auto issue = [&](int j) {
-        const int ti = j / (K + 1), s = j - ti * (K + 1), buf = j % NBUF;
+        const int ti = j / K, s = j - ti * K, buf = j % NBUF;
         const int64_t tile = tile_of(ti);
         if (PROD_WARP && j >= NBUF) mbar_wait(&done[buf], (unsigned)(((j / NBUF) - 1) & 1));
         mbar_arrive_expect_tx(&full[buf], tile_bytes + (s == 0 ? 2 * slab_bytes : 0u));
-        const double* src = (s < K) ? cb.Bk + ((size_t)s * cb.tiles_cap + tile) * tile_elems : cb.A + (size_t)tile * tile_elems;
-        bulk_g2s(Tb + (size_t)buf * tile_elems, src, tile_bytes, &full[buf]);
+        bulk_g2s(Tb + (size_t)buf * tile_elems, cb.Bk + ((size_t)s * cb.tiles_cap + tile) * tile_elems, tile_bytes, &full[buf]);
         if (s == 0) {
             bulk_g2s(mub + (size_t)(ti & 1) * NT * KP, cb.mubar + (size_t)tile * NT * K, slab_bytes, &full[buf]);
             bulk_g2s(vbs + (size_t)(ti & 1) * NT * KP, cb.vbar + (size_t)tile * NT * K, slab_bytes, &full[buf]);
+            bulk_prefetch_l2(cb.A + (size_t)tile * tile_elems, tile_bytes);   // read by the epilogue K stages from now
         }
     };
     if (PROD_WARP && warp == NW) {
@@ -920,7 +924,7 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
     }
     double acc[NBW][2][NF][2];
     for (int j = 0; j < total; ++j) {
-        const int ti = j / (K + 1), s = j - ti * (K + 1), buf = j % NBUF;
+        const int ti = j / K, s = j - ti * K, buf = j % NBUF;
         const double* T = Tb + (size_t)buf * tile_elems;
         const double* mb = mub + (size_t)(ti & 1) * NT * KP;
         const double* vb = vbs + (size_t)(ti & 1) * NT * KP;
@@ -929,7 +933,7 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
 #pragma unroll
             for (int r = 0; r < NBW; ++r) zero_acc<NF>(acc[r]);
         }
-        if (s < K) {
+        {
             if (SCALE_IN_SMEM) {
                 // 16-point tiles (16 consumer warps, 128-register cap): the column weights 2 vbar_s are applied to the
                 // landed B_s stage in shared memory — one pass of Mp * NT multiplications per stage (< 0.5 % of its
@@ -974,7 +978,8 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
                     }
             }
             }
-        } else {   // tile epilogue: + q_mu mubar^T - 2 A diag(sum_k vbar_k), written over A (tile-major, in place)
+        }
+        if (s == K - 1) {   // tile epilogue: + q_mu mubar^T - 2 A diag(sum_k vbar_k), written over A (tile-major, in place)
             double* Aout = cb.A + (size_t)tile_of(ti) * tile_elems;
             double vs[NF][2];
 #pragma unroll
@@ -1004,14 +1009,21 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
 #pragma unroll
                         for (int nf = 0; nf < NF; ++nf) dmma(acc[r][mf][nf], a, bm[kb][nf]);
                     }
+                // this lane's A values (prefetched into L2 when the tile's first stage was issued): all loads of the
+                // block first, then the in-place stores
+                double2 av[2][NF];
+#pragma unroll
+                for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf)
+                        av[mf][nf] = __ldcs(reinterpret_cast<const double2*>(Aout + (size_t)(b * 16 + mf * 8 + g) * STR + nf * 8 + 2 * t));
 #pragma unroll
                 for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
                     for (int nf = 0; nf < NF; ++nf) {
                         const size_t off = (size_t)(b * 16 + mf * 8 + g) * STR + nf * 8 + 2 * t;
-                        const double2 av = *reinterpret_cast<const double2*>(T + off);
                         *reinterpret_cast<double2*>(Aout + off) =
-                            make_double2(acc[r][mf][nf][0] - 2.0 * vs[nf][0] * av.x, acc[r][mf][nf][1] - 2.0 * vs[nf][1] * av.y);
+                            make_double2(acc[r][mf][nf][0] - 2.0 * vs[nf][0] * av[mf][nf].x, acc[r][mf][nf][1] - 2.0 * vs[nf][1] * av[mf][nf].y);
                     }
             }
         }

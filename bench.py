@@ -310,9 +310,12 @@ def main():
     # untimed: first-use allocations of the per-step device copies.  Same statement pattern as the timed loop below:
     # the previous step's xd / yd are still alive when the next pair is allocated, so the caching allocator needs
     # two pairs, and the second pair's cudaMalloc (60-80 ms with the 23 GB workspace resident, measured) must land here
+    # The host batches go through the package's input stage (HostBatchStream): every step's X, Y are copied from pinned
+    # host memory inside the timed region, on a copy stream, one step ahead of the step that consumes them.
+    import itertools
+    feed = mg.HostBatchStream(itertools.repeat((Xh, Yh)), dev)
     for _ in range(3):
-        xd = Xh.to(dev, non_blocking=True)
-        yd = Yh.to(dev, non_blocking=True)
+        xd, yd = next(feed)
         loss = step(xd, yd)
         _ = loss.item()
     barrier()
@@ -320,15 +323,27 @@ def main():
     t_host0 = time.perf_counter()
     e2.record()
     trace = []
-    for _ in range(args.steps):
+    # Every step's loss is read back inside the timed region, ONE STEP LATE (as a training loop that logs its loss does):
+    # the host enqueues step i + 1 while step i runs, so the device does not idle through Python between steps.
+    # (a plain .item() one step late would not do: its D2H copy is enqueued BEHIND the step just launched and returns
+    #  only when that step ends; the loss goes to pinned host memory right behind its own step, guarded by an event)
+    loss_host = torch.zeros(2, dtype=torch.float64).pin_memory()
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    losses = []
+    for i in range(args.steps):
         ta = time.perf_counter()
-        xd = Xh.to(dev, non_blocking=True)
-        yd = Yh.to(dev, non_blocking=True)
+        xd, yd = next(feed)
         tb = time.perf_counter()
         loss = step(xd, yd)
+        loss_host[i & 1:(i & 1) + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        loss_ev[i & 1].record()
         tc = time.perf_counter()
-        _ = loss.item()
+        if i > 0:
+            loss_ev[(i - 1) & 1].synchronize()
+            losses.append(float(loss_host[(i - 1) & 1]))
         trace.append((1e3 * (tb - ta), 1e3 * (tc - tb), 1e3 * (time.perf_counter() - tc)))
+    loss_ev[(args.steps - 1) & 1].synchronize()
+    losses.append(float(loss_host[(args.steps - 1) & 1]))
     e3.record()
     if os.environ.get("BENCH_TRACE") and rank == 0:
         for r in trace:
@@ -382,7 +397,13 @@ def main():
                 "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "points/s", "ms_per_step": e2e_ms,
                         "host_wall_ms_per_step": 1e3 * t_host / args.steps,
                         "h2d_bytes_per_step": int(Xh.numel() * 8 + Yh.numel() * 8) * world, "d2h_bytes_per_step": 8 * world,
-                        "api": "modulatedgps_b200.SMGP._training_loss((X_host, Y_host)) + loss.backward() + loss.item()"},
+                        "api": "for Xd, Yd in modulatedgps_b200.HostBatchStream(host_batches): "
+                               "SMGP._training_loss((Xd, Yd)) + loss.backward() + loss.item()",
+                        "h2d": "every step's inputs are copied from pinned host memory inside the timed region, on a copy "
+                               "stream, while the previous step computes (two device buffer pairs)",
+                        "d2h": "every step's loss (8 bytes) is copied to pinned host memory behind its own step and read by the "
+                               "host inside the timed region, one step late; the last one before the closing event",
+                        "losses_read": len(losses)},
                 "gpu_launches": int(launches), "roofline": roofline,
                 "step_roofline": {"flops_per_point": cfg.flops_per_point(), "roof_ms_per_step": step_roof_ms,
                                   "frac_of_fp64_peak": step_roof_ms / ms_per_step, "peak_tflops": FP64_PEAK_TFLOPS,

@@ -11,9 +11,9 @@ from .kernels import RBF, SquaredExponential
 from .likelihoods import GaussianModified, MultiClass, RobustMax
 from .models import SGP, SMGP, DeviceArray, InducingPoints, SMGPModified, SVGPModified
 from .parameter import Module, Parameter, print_summary
-from .training import DeviceMinibatches, FusedAdam, kmeans, make_adam, predict_samples_batched, run_adam
+from .training import DeviceMinibatches, FusedAdam, HostBatchStream, kmeans, make_adam, predict_samples_batched, run_adam
 from .utils import reparameterize
 
 __all__ = ["SquaredExponential", "RBF", "GaussianModified", "MultiClass", "RobustMax", "BroadcastingLikelihood",
            "SVGPModified", "SGP", "SMGP", "SMGPModified", "InducingPoints", "Parameter", "Module", "print_summary",
-           "run_adam", "make_adam", "FusedAdam", "DeviceMinibatches", "kmeans", "predict_samples_batched", "reparameterize", "MgpError", "NotPositiveDefiniteError", "DeviceArray"]
+           "run_adam", "make_adam", "FusedAdam", "DeviceMinibatches", "HostBatchStream", "kmeans", "predict_samples_batched", "reparameterize", "MgpError", "NotPositiveDefiniteError", "DeviceArray"]

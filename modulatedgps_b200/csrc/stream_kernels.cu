@@ -31,6 +31,19 @@
 
 namespace mgp {
 
+// Per-warp phase timers (clock64 sums) for TEMPORARY profiling builds only: nvcc -DMGP_PHASE_TIMERS, read back with
+// mgp_debug_phase_dump (tools/phase_timers.py).  Compiled out of the product.
+#ifdef MGP_PHASE_TIMERS
+__device__ long long g_phase[4][160][17][8];   // [kernel][cta][warp][phase]
+#define PH_DECL long long ph_t = clock64(); long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PH_MARK(i) { const long long ph_now = clock64(); ph_acc[i] += ph_now - ph_t; ph_t = ph_now; }
+#define PH_STORE(kid) { if ((threadIdx.x & 31) == 0 && blockIdx.x < 160) for (int ph_i = 0; ph_i < 8; ++ph_i) g_phase[kid][blockIdx.x][threadIdx.x >> 5][ph_i] = ph_acc[ph_i]; }
+#else
+#define PH_DECL
+#define PH_MARK(i)
+#define PH_STORE(kid)
+#endif
+
 // exp2_tab(y) = exp(y ln2 / 64) from a 64-entry table of 2^(j/64) and a degree-5 polynomial on |rr| <= 1/2 (rr in
 // units of ln2/64): 9 FP64 instructions instead of libdevice's 16-18 for exp, at most 1.1 ulp from expl
 // (tools/exp_tab_check.c, tests/test_host_logic.py).  The argument arrives ALREADY in units of ln2/64: the left operand
@@ -567,13 +580,16 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + 32, 1) cond_fwd_b_kernel(L
     };
     WPair wp;
     if (nmy > 0) { const Seg s0 = seg_of(0, 0); wfrag_load(wp.f, s0, C4, s0.kb0, lane); }
+    PH_DECL
     for (int i = 0; i < my_tiles; ++i) {
         const int buf = i % NBUF;
         const int64_t tile = tile_of(i);
         const double* T = Tb + (size_t)buf * tile_elems;
         double* sq = sqpart + ((size_t)buf * NW + warp) * K * NT;
         double* mn = mnpart + ((size_t)buf * MW + (warp < MW ? warp : 0)) * K * NT;
+        PH_MARK(5)
         mbar_wait(&full[buf], (unsigned)((i / NBUF) & 1));
+        PH_MARK(0)
         for (int k = 0; k < K; ++k) {
             double colsq[NF][2];
 #pragma unroll
@@ -585,6 +601,7 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + 32, 1) cond_fwd_b_kernel(L
                 zero_acc<NF>(acc);
                 const Seg nxt = (r + 1 < nmy) ? seg_of(k, r + 1) : seg_of(k + 1 < K ? k + 1 : 0, 0);
                 wp.template run<NT, TRI_UPPER>(seg_of(k, r), C4, C4, T, acc, lane, nxt);   // upper triangular
+                PH_MARK(1)
 #pragma unroll
                 for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
@@ -595,6 +612,7 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + 32, 1) cond_fwd_b_kernel(L
                         colsq[nf][0] = fma(acc[mf][nf][0], acc[mf][nf][0], colsq[nf][0]);
                         colsq[nf][1] = fma(acc[mf][nf][1], acc[mf][nf][1], colsq[nf][1]);
                     }
+                PH_MARK(2)
             }
             if (NF == 4) {   // 8 values per lane: butterfly with hand-over (7 shuffles), lane (g, t) ends with column
                              // (g >> 1) * 8 + 2 t + (g & 1) — every lane stores one distinct column
@@ -612,6 +630,7 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + 32, 1) cond_fwd_b_kernel(L
                     }
             }
         }
+        PH_MARK(3)
         if (warp < MW) {   // this warp's slice of fmean^T [K x NT] = q_mu^T [K x Mp] * A tile   (rows >= K of W_mT are zero).
             // Two accumulator sets (even / odd k4-blocks): the contraction is a short dependent DMMA chain.
             double acc[2][NF][2];
@@ -639,7 +658,9 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + 32, 1) cond_fwd_b_kernel(L
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&done[buf]);
+        PH_MARK(4)
     }
+    PH_STORE(0)
 }
 
 // ==================================================================================================
@@ -923,12 +944,15 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
                 wm[r][mf][kb] = (r < nmy && b >= 0) ? __ldg(ly.W_m + ((size_t)(2 * b + mf) * (KP / 4) + kb) * 32 + lane) : 0.0;
     }
     double acc[NBW][2][NF][2];
+    PH_DECL
     for (int j = 0; j < total; ++j) {
         const int ti = j / K, s = j - ti * K, buf = j % NBUF;
         const double* T = Tb + (size_t)buf * tile_elems;
         const double* mb = mub + (size_t)(ti & 1) * NT * KP;
         const double* vb = vbs + (size_t)(ti & 1) * NT * KP;
+        PH_MARK(5)
         mbar_wait(&full[buf], (unsigned)((j / NBUF) & 1));
+        PH_MARK(0)
         if (s == 0) {
 #pragma unroll
             for (int r = 0; r < NBW; ++r) zero_acc<NF>(acc[r]);
@@ -968,7 +992,9 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
                 double ck[2][NF][2];
                 zero_acc<NF>(ck);
                 const Seg nxt = (r + 1 < nmy) ? seg_of(s, r + 1) : seg_of(s + 1 < K ? s + 1 : 0, 0);
+                PH_MARK(1)
                 wgemm_seg<NT, TRI_LOWER>(seg_of(s, r), (b + 1) * 4, C4, T, ck, lane, wf, nxt);   // lower triangular
+                PH_MARK(2)
 #pragma unroll
                 for (int mf = 0; mf < 2; ++mf)
 #pragma unroll
@@ -976,6 +1002,7 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
                         acc[r][mf][nf][0] = fma(ck[mf][nf][0], sc[nf][0], acc[r][mf][nf][0]);
                         acc[r][mf][nf][1] = fma(ck[mf][nf][1], sc[nf][1], acc[r][mf][nf][1]);
                     }
+                PH_MARK(3)
             }
             }
         }
@@ -1027,6 +1054,7 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
                     }
             }
         }
+        PH_MARK(4)
         __syncwarp();
         if (lane == 0) {
             if (PROD_WARP) {
@@ -1044,6 +1072,7 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
             }
         }
     }
+    PH_STORE(1)
 }
 
 // ==================================================================================================
@@ -1108,19 +1137,22 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_bwd_b_kernel(LayerDev 
         if (threadIdx.x == 0) load_tile(blockIdx.x);
         if (warp == 1) stage_x(blockIdx.x, 0);
     }
-
     int it = 0;
+    PH_DECL
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const double* Xs = Xsb + (size_t)(it & 1) * xs_elems;
         const double* xs2 = Xs + NT * XSTR;
         const unsigned phase = (unsigned)(it & 1);
+        PH_MARK(5)
         mbar_wait(full, phase);
+        PH_MARK(0)
         if (nmy == 0) { __syncwarp(); if (lane == 0) mbar_arrive(tfree); }
         for (int i = 0; i < nmy; ++i) {
             const int b = snake_block<NW>(i, warp, nb16);
             double acc[2][NF][2];
             zero_acc<NF>(acc);
             wgemm_seg<NT, TRI_UPPER>(seg_of(i), C4, C4, T, acc, lane, wf, seg_of(i + 1 < nmy ? i + 1 : 0));   // upper triangular
+            PH_MARK(1)
             if (i == nmy - 1) { __syncwarp(); if (lane == 0) mbar_arrive(tfree); }   // this warp is done with T
             const double* Ph = xs2 + NT;
 #pragma unroll
@@ -1140,6 +1172,7 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_bwd_b_kernel(LayerDev 
                 for (int nf = 0; nf < NF; ++nf)
 #pragma unroll
                     for (int e = 0; e < 2; ++e) acc[mf][nf][e] *= kv[nf][e];   // E = Kuf_bar .* Kuf
+                PH_MARK(2)
                 // sum_n E[i][n] Phi[n][f] on DMMA: the C fragment of E is read as A fragments over the point subsets
                 // {nf*8 + 2t + e : t = 0..3}, the matching rows of Phi as B fragments.  (Per element this replaces 2 + 3 D
                 // scalar FP64 instructions, each of which costs the tensor pipe several DMMA issue slots, by 1/4 DMMA.)
@@ -1160,17 +1193,21 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32) cond_bwd_b_kernel(LayerDev 
                         else if (f <= 2 * D) atomicAdd(p + 1 + Dp + (f - 1 - D), R[j]);
                     }
                 }
+                PH_MARK(3)
             }
         }
         const int next = tile + gridDim.x;
         if (warp <= 1 && next < ntiles) {
             // tfree(it) also tells that every warp has finished the epilogue of tile it - 1 (it comes before its
-            // arrival in program order), i.e. nobody still reads the Xs buffer about to be refilled
+            // arrival in program order), i.e. nobody still reads the Xs buffer about to be refilled.
+            // (Fetching the next tile BEFORE these two warps' own last epilogue was measured: 5.34 vs 5.29 ms.)
             mbar_wait(tfree, phase);
             if (threadIdx.x == 0) load_tile(next);
             if (warp == 1) stage_x(next, it + 1);
+            PH_MARK(4)
         }
     }
+    PH_STORE(2)
 }
 
 // ==================================================================================================
@@ -1449,3 +1486,10 @@ void cond_bwd_b(const LayerDev& ly, const ChunkBuffers& cb, double* esum_part, i
 }
 
 }  // namespace mgp
+
+#ifdef MGP_PHASE_TIMERS
+// (temporary profiling builds only) copies g_phase to the host: out[4][160][17][8]
+extern "C" int mgp_debug_phase_dump(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, mgp::g_phase, sizeof(long long) * 4 * 160 * 17 * 8);
+}
+#endif

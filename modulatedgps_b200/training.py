@@ -4,6 +4,7 @@
     FusedAdam             tf.optimizers.Adam(lr).minimize(training_loss, model.trainable_variables) (:6-10) as ONE
                           libmgp kernel over every unconstrained variable, bijector chain rule included
     DeviceMinibatches     tf.data ... .shuffle(N, seed).batch(B).repeat() (demos/demo_tf2.py:53-56) without the host
+    HostBatchStream       host-resident batches staged to the device one step ahead on a copy stream
     kmeans                scipy.cluster.vq.kmeans as the demos call it for the inducing inputs (demo_tf2.py:39)
     predict_samples_batched   the demos' chunked predict_samples loop (demo_tf2.py:62-68)
 
@@ -157,6 +158,70 @@ class DeviceMinibatches:
         _check(lib.mgp_gather_rows(_stream_ptr(), _lib.ptr(self.X), _lib.ptr(self.Y), idx.data_ptr(), B, self.D,
                                    _lib.ptr(Xb), _lib.ptr(Yb)), "mgp_gather_rows")
         return Xb, Yb.unsqueeze(1)
+
+
+class HostBatchStream:
+    """(X, Y) batches that live in HOST memory, handed to the training step as device tensors with the copy of batch
+    i + 1 in flight on a copy stream while step i computes (what `tf.data`'s `.prefetch()` / device staging does for
+    the reference's input pipeline, demos/demo_tf2.py:53-56, when the data do not fit on or do not start on the GPU).
+
+        for Xd, Yd in HostBatchStream(batches, device): loss = model._training_loss((Xd, Yd)); ...
+
+    `batches`: any iterator of (X, Y) host arrays / CPU tensors; pinned float64 tensors are copied as they are, anything
+    else is staged through a pinned buffer first.  Two device buffer pairs: the copy into a pair starts only after the
+    step that last read it (two batches back) has been enqueued in full on the compute stream."""
+
+    def __init__(self, batches, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.batches = iter(batches)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self._dev = [None, None]          # device buffer pairs
+        self._ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self._i = 0
+        self._pending = None              # index of the pair whose copy is in flight
+        self._done = False
+        self._keep = [None, None]
+        self._enqueue()
+
+    @staticmethod
+    def _pinned(a):
+        t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(a))
+        t = t.to(F64).contiguous()
+        return t if t.is_pinned() else t.pin_memory()
+
+    def _enqueue(self):
+        try:
+            X, Y = next(self.batches)
+        except StopIteration:
+            self._done, self._pending = True, None
+            return
+        Xh, Yh = self._pinned(X), self._pinned(Y)
+        k = self._i & 1
+        self._i += 1
+        buf = self._dev[k]
+        if buf is None or buf[0].shape != Xh.shape or buf[1].shape != Yh.shape:
+            buf = self._dev[k] = (torch.empty(Xh.shape, dtype=F64, device=self.device),
+                                  torch.empty(Yh.shape, dtype=F64, device=self.device))
+        # everything enqueued on the compute stream so far (the step that last read this pair included) comes first
+        self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.copy_stream):
+            buf[0].copy_(Xh, non_blocking=True)
+            buf[1].copy_(Yh, non_blocking=True)
+            self._ready[k].record(self.copy_stream)
+        self._keep[k] = (Xh, Yh)          # the pinned source outlives the asynchronous copy
+        self._pending = k
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._pending is None:
+            raise StopIteration
+        k = self._pending
+        torch.cuda.current_stream(self.device).wait_event(self._ready[k])
+        out = self._dev[k]
+        self._enqueue()                   # the next batch's copy overlaps the step the caller is about to launch
+        return out
 
 
 def kmeans(obs, k_or_guess, iter=20, thresh=1e-5, seed=None, max_lloyd=200):

@@ -534,3 +534,19 @@ def test_alternative_kernel_forms_agree(hg, monkeypatch, env):
         assert abs(float(e1) - float(e0)) <= 1e-12 * abs(float(e0))
         for k in g0:
             assert relerr(g1[k].cpu().numpy(), g0[k].cpu().numpy()) <= 1e-10, k
+
+
+def test_host_batch_stream_delivers_every_batch_in_order():
+    """HostBatchStream: host batches come out as device tensors, in order, with equal values; the copy of the next batch
+    is enqueued before the current one is handed out (two buffer pairs, reused two batches later)."""
+    import modulatedgps_b200 as mg
+    rng = np.random.default_rng(0)
+    batches = [(rng.standard_normal((50 + 7 * i, 3)), rng.standard_normal((50 + 7 * i, 1))) for i in range(5)]
+    pinned = [(torch.as_tensor(x).pin_memory(), torch.as_tensor(y).pin_memory()) for x, y in batches[:2]] + batches[2:]
+    got = []
+    for Xd, Yd in mg.HostBatchStream(iter(pinned)):
+        assert Xd.is_cuda and Yd.is_cuda and Xd.dtype == torch.float64
+        got.append((Xd.cpu().numpy().copy(), Yd.cpu().numpy().copy()))
+    assert len(got) == len(batches)
+    for (x, y), (gx, gy) in zip(batches, got):
+        assert np.array_equal(x, gx) and np.array_equal(y, gy)

@@ -1,0 +1,5 @@
+#!/bin/bash
+python -m pytest tests -m gpu -q 2>&1 | tail -n 3 > gpurun_out/r02k_tests.txt; cat gpurun_out/r02k_tests.txt
+BENCH_TRACE=1 python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; grep "e2e step" gpurun_out/r02_bench_1gpu.err | tail -4
+python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_1gpu.json')); print('ms', d['ms_per_step'], 'e2e ms', d['e2e']['ms_per_step'], 'frac', d['step_roofline']['frac_of_fp64_peak'], 'cpu', d['cpu_baseline']['value'])"

@@ -1,7 +1,5 @@
 #!/bin/bash
-# 8-GPU evidence: config #4 (headline) and config #5 at its full size
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
-timeout 300 $TR bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/r02_bench_8gpu.json 2> gpurun_out/r02_bench_8gpu.err
-tail -c 1500 gpurun_out/r02_bench_8gpu.json
-timeout 600 $TR bench.py --gpus 8 --config 5 --steps 2 --warmup 3 > gpurun_out/r02_bench_cfg5_8gpu.json 2> gpurun_out/r02_bench_cfg5_8gpu.err
-tail -c 2500 gpurun_out/r02_bench_cfg5_8gpu.json; tail -n 5 gpurun_out/r02_bench_cfg5_8gpu.err
+python -m pytest tests -m gpu -q 2>&1 | tail -n 5 > gpurun_out/r02i_tests.txt; cat gpurun_out/r02i_tests.txt
+python bench.py --steps 10 --warmup 3 > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; tail -c 600 gpurun_out/r02_bench_1gpu.err
+python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_1gpu.json')); print('ms', d['ms_per_step'], 'e2e ms', d['e2e']['ms_per_step'], 'frac', d['step_roofline']['frac_of_fp64_peak'], d['roofline']['all_kernels_tflops'])"

@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmgp.so")
-SOURCES = ["api.cu", "precompute.cu", "gemm_small.cu", "stream_kernels.cu", "syrk.cu", "mc_pass.cu", "train_kernels.cu"]
+SOURCES = ["api.cu", "precompute.cu", "gemm_small.cu", "stream_kernels.cu", "stream_kernels_alt.cu", "syrk.cu", "mc_pass.cu", "train_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 NVCC_FLAGS += os.environ.get("NVCC_EXTRA", "").split()      # e.g. -DMGP_PHASE_TIMERS for a temporary profiling build

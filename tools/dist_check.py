@@ -5,7 +5,10 @@
 Every rank holds a contiguous shard of a config-#4-style workload.  The ELBO and every gradient from
   (a) torch.distributed all_reduce between mgp_elbo_local and mgp_elbo_finish, and
   (b) the communicator attached to the libmgp context (mgp_ctx_set_comm: ncclAllReduce issued by the C library)
-must agree with each other bit for bit and with (c) the single-GPU evaluation of all points on rank 0 to 1e-11.
+must agree with (c) the single-GPU evaluation of all points on rank 0 to 1e-11, and with each other — bit for bit on 2
+ranks (a two-term sum has one order), to 1e-12 on more: the torch form reduces ONE buffer, libmgp two (per layer), and
+NCCL picks its algorithm and chunking per call, so the summation order over > 2 ranks differs in the last bit (8 GPUs:
+not bit-identical, both 5e-12 from the single-GPU evaluation; profiles/r02_dist_check_8gpu.json).
 Prints one JSON line on rank 0."""
 import json
 import os
@@ -50,18 +53,25 @@ def main():
     a, b = run("torch"), run("nccl")
     c = run(None) if rank == 0 else None
     same = all(np.array_equal(a[k], b[k]) for k in a)
-    worst = 0.0
+    ab = max(float(np.max(np.abs(a[k] - b[k])) / max(np.max(np.abs(b[k])), 1e-300)) for k in a)
+    worst, worst_torch = 0.0, 0.0
     if rank == 0:
         for k in a:
             den = max(np.max(np.abs(c[k])), 1e-300)
             worst = max(worst, float(np.max(np.abs(b[k].reshape(c[k].shape) - c[k])) / den))
-    flag = torch.tensor([1 if same else 0], device=dev)
+            worst_torch = max(worst_torch, float(np.max(np.abs(a[k].reshape(c[k].shape) - c[k])) / den))
+    close = same if world == 2 else ab <= 1e-12
+    flag = torch.tensor([1 if same else 0, 1 if close else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    abt = torch.tensor([ab], dtype=torch.float64, device=dev)
+    dist.all_reduce(abt, op=dist.ReduceOp.MAX)
+    ok = bool(int(flag[1])) and worst <= 1e-11 and worst_torch <= 1e-11
     if rank == 0:
-        print(json.dumps({"world": world, "torch_equals_nccl_bitwise_on_every_rank": bool(int(flag)),
-                          "worst_rel_err_vs_single_gpu": worst, "elbo": float(b["elbo"]), "ok": bool(int(flag)) and worst <= 1e-11}))
+        print(json.dumps({"world": world, "torch_equals_nccl_bitwise_on_every_rank": bool(int(flag[0])),
+                          "torch_vs_nccl_worst_rel_diff": float(abt), "worst_rel_err_vs_single_gpu": worst,
+                          "worst_rel_err_vs_single_gpu_torch_collective": worst_torch, "elbo": float(b["elbo"]), "ok": ok}))
     dist.destroy_process_group()
-    return 0 if (bool(int(flag)) and (rank != 0 or worst <= 1e-11)) else 1
+    return 0 if (bool(int(flag[1])) and (rank != 0 or ok)) else 1
 
 
 if __name__ == "__main__":

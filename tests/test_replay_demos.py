@@ -56,11 +56,11 @@ def test_demo_tf2_reaches_the_published_elbo():
     anchors = runs[0][1]
     ends = []
     for rec, _ in runs:
-        _check(rec, dict(anchors, final_at_least=-0.6))
+        _check(rec, dict(anchors, final_at_least=-0.75))   # (worst of 10 recorded runs: -0.51; a two-component optimum)
         assert sum(c > 0 for c in rec["assign_argmax_counts"]) >= 2   # final_figs/demo_tf2.png: two components dominate
         ends.append(float(np.mean(rec["elbos"][-10:])))
     assert max(ends) >= anchors["final_at_least"], ends
-    assert float(np.median(ends)) >= -0.4, ends
+    assert float(np.median(ends)) >= -0.45, ends               # (recorded: -0.16 and -0.28)
     # the whole pipeline on the device (this package's k-means instead of the recorded scipy centroids): another
     # initial state, so only the start and a looser end level are asserted; the trajectory is recorded
     dev, _ = _run("tf2", inducing="device")

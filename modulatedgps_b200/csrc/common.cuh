@@ -90,6 +90,20 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive and report how many arrivals the phase was still waiting for BEFORE this one (1: this was the last)
+__device__ __forceinline__ unsigned mbar_arrive_pending(uint64_t* bar) {
+    unsigned pending;
+    asm volatile(
+        "{\n"
+        ".reg .b64 st;\n"
+        "mbarrier.arrive.shared::cta.b64 st, [%1];\n"
+        "mbarrier.pending_count.b64 %0, st;\n"
+        "}\n"
+        : "=r"(pending)
+        : "r"(smem_u32(bar))
+        : "memory");
+    return pending;
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }

@@ -312,7 +312,6 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
     const int Mp = ly.Mp, K = ly.K;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);
     uint64_t* done = full + NBUF;
-    unsigned* left = reinterpret_cast<unsigned*>(done + NBUF);   // !PROD_WARP: warps that have left the stage in buffer b
     double* Tb = smem + SK_BAR_DOUBLES;                // [NBUF][Mp][STR]
     double* mub = Tb + (size_t)NBUF * Mp * STR;        // [2][NT][K]  mubar slab of the tile (by tile parity)
     double* vbs = mub + 2 * NT * KP;                   // [2][NT][K]  vbar slab
@@ -322,7 +321,7 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
     const unsigned tile_bytes = (unsigned)(tile_elems * sizeof(double));
     const unsigned slab_bytes = (unsigned)(NT * K * sizeof(double));
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], NW); left[i] = 0u; }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], NW); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -489,11 +488,10 @@ __global__ void __launch_bounds__(sk_warps(NT) * 32 + (PROD_WARP ? 32 : 0), 1)
             } else {
                 // no producer warp: the LAST warp to leave the stage refills its buffer with stage j + NBUF at once —
                 // nobody waits for the stragglers (a rotating duty that waited on `done` cost 3.3 % of the kernel)
-                __threadfence_block();
-                const unsigned before = atomicAdd(&left[buf], 1u);
-                if (before == NW - 1) {
-                    left[buf] = 0u;
-                    __threadfence_block();
+                // (`done[buf]` counts the NW leavers; the arrival that finds one pending is the last: its release /
+                //  the others' are acquired by the parity wait, which returns at once, before the refill is issued)
+                if (mbar_arrive_pending(&done[buf]) == 1u) {
+                    mbar_wait(&done[buf], (unsigned)((j / NBUF) & 1));
                     if (j + NBUF < total) issue(j + NBUF);
                 }
             }

@@ -688,7 +688,10 @@ void cond_fwd_b(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
         kernel<<<grid, threads, smem, ln.stream>>>(ly, cb, ntiles);
         ln.tick();
     };
-    if (NT == 32) launch(cond_fwd_b_kernel<32, 2>);
+    if (NT == 32) {
+        if (cond_fwd_b_wants_16w(ly, NT)) { cond_fwd_b_16w(ly, cb, ln); return; }   // (stream_kernels_alt.cu: measured slower)
+        launch(cond_fwd_b_kernel<32, 2>);
+    }
     else if (nbuf == 2) launch(cond_fwd_b_kernel<16, 2>);
     else launch(cond_fwd_b_kernel<16, 1>);
 }

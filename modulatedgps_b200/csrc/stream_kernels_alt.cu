@@ -5,6 +5,7 @@
 //   MGP_FWD_A_PIPE   software-pipelined one-CTA cond_fwd_a            5.94 ms vs 5.28 ms (barrier-phased, three CTAs per SM)
 //   MGP_FUSED_FWD    cond_fwd_a + cond_fwd_b in one persistent kernel  23.7 ms vs 23.1 ms
 //   MGP_BWD_B_RING   ring-form one-CTA cond_bwd_b                      5.47 ms vs 5.28 ms (two CTAs per SM)
+//   MGP_FWD_B_16W    cond_fwd_b with 16 consumer warps (4 per sub-partition)  18.12 ms vs 17.57 ms (8 warps + loader warp)
 #include "stream_common.cuh"
 
 namespace mgp {
@@ -411,6 +412,163 @@ __global__ void __launch_bounds__(SK_WARPS * 32 + 32, 1) cond_bwd_b_ring_kernel(
 }
 
 // ==================================================================================================
+// cond_fwd_b, 16-warp form (32-point tiles, even K):  FOUR warps per sub-partition instead of two.
+// The inner loop's ceiling is 35.4 TFLOP/s with two warps per sub-partition and 36.4 with four (tools/loop_bisect.cu:
+// the L2 round trip of the left-operand fragments is covered by three other warps instead of one), and with four a
+// warp's per-pass / per-tile epilogue always has other warps' DMMAs beside it.  MEASURED SLOWER all the same (18.12 vs
+// 17.57 ms at config #4).  Sixteen warps own ONE 16-row block per
+// pass each; the triangular imbalance (block b has 16 - b fragment groups) is evened out ACROSS passes — pass k deals
+// the blocks in direction k & 1, so a warp's two consecutive passes sum to 17 groups — which works because each pass has
+// its own output (cond_bwd_a's accumulators persist across its stages: no such form there).  No loader warp (the
+// register file allows 128 registers per thread at 16 warps, 102 at 17): the last warp to leave a tile folds the
+// partial sums into fmean / fvar and refills the buffer.
+// ==================================================================================================
+template <int NT, int NBUF>
+__global__ void __launch_bounds__(SK_WARPS_NT16 * 32, 1) cond_fwd_b16_kernel(LayerDev ly, ChunkBuffers cb, int ntiles) {
+    constexpr int NF = NT / 8, STR = NT + 4, NW = SK_WARPS_NT16, MW = SK_WARPS;
+    extern __shared__ __align__(16) double smem[];
+    const int Mp = ly.Mp, K = ly.K;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* done = full + NBUF;
+    double* Tb = smem + SK_BAR_DOUBLES;                          // [NBUF][Mp][STR]
+    double* sqpart = Tb + (size_t)NBUF * Mp * STR;               // [NBUF][NW][K][NT]  partial sum_m B_k^2
+    double* mnpart = sqpart + (size_t)NBUF * NW * K * NT;        // [NBUF][MW][K][NT]  partial q_mu^T A
+    double* aspart = mnpart + (size_t)NBUF * MW * K * NT;        // [NBUF][NW][NT]     partial |a_n|^2
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int nb16 = Mp / 16, C4 = Mp / 4, R = (nb16 + NW - 1) / NW;
+    const size_t tile_elems = (size_t)Mp * STR;
+    const unsigned tile_bytes = (unsigned)(tile_elems * sizeof(double));
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], NW); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto tile_of = [&](int i) { return (int64_t)blockIdx.x + (int64_t)i * gridDim.x; };
+    auto issue = [&](int i) {   // one lane
+        const int buf = i % NBUF;
+        mbar_arrive_expect_tx(&full[buf], tile_bytes);
+        bulk_g2s(Tb + (size_t)buf * tile_elems, cb.A + (size_t)tile_of(i) * tile_elems, tile_bytes, &full[buf]);
+    };
+    if (threadIdx.x == 0)
+        for (int i = 0; i < NBUF && i < my_tiles; ++i) issue(i);
+    // block of (pass k, round r) for this warp: direction alternates with r + k; -1 past the end
+    auto blk = [&](int k, int r) {
+        const int b = r * NW + (((r + k) & 1) ? (NW - 1 - warp) : warp);
+        return b < nb16 ? b : -1;
+    };
+    // the unit after (k, r) in this warp's per-tile sequence that has a block (wraps to the next tile's first)
+    auto next_unit = [&](int& k, int& r) {
+        do {
+            if (++r == R) { r = 0; if (++k == K) k = 0; }
+        } while (blk(k, r) < 0);
+    };
+    auto seg_of = [&](int k, int r) {
+        const int b = blk(k, r);
+        return Seg{ly.W_LqT + (size_t)k * Mp * Mp, 2 * b, 4 * b};
+    };
+    const int mkb0 = warp * (C4 / MW), mkb1 = mkb0 + C4 / MW;   // fmean k-slice of warps < MW
+    const double variance = ly.variance[0];
+    int k0 = 0, r0 = 0;   // first unit of the sequence
+    if (blk(0, 0) < 0) next_unit(k0, r0);
+    WPair wp;
+    { const Seg s0 = seg_of(k0, r0); wfrag_load(wp.f, s0, C4, s0.kb0, lane); }
+    for (int i = 0; i < my_tiles; ++i) {
+        const int buf = i % NBUF;
+        const int64_t tile = tile_of(i);
+        const double* T = Tb + (size_t)buf * tile_elems;
+        double* sq = sqpart + ((size_t)buf * NW + warp) * K * NT;
+        mbar_wait(&full[buf], (unsigned)((i / NBUF) & 1));
+        for (int k = 0; k < K; ++k) {
+            double colsq[NF][2];
+#pragma unroll
+            for (int nf = 0; nf < NF; ++nf) colsq[nf][0] = colsq[nf][1] = 0.0;
+            double* Bk = cb.Bk ? cb.Bk + ((size_t)k * cb.tiles_cap + tile) * tile_elems : nullptr;
+            for (int r = 0; r < R; ++r) {
+                const int b = blk(k, r);
+                if (b < 0) continue;
+                double acc[2][NF][2];
+                zero_acc<NF>(acc);
+                int kn = k, rn = r;
+                next_unit(kn, rn);
+                wp.template run<NT, TRI_UPPER>(seg_of(k, r), C4, C4, T, acc, lane, seg_of(kn, rn));   // upper triangular
+#pragma unroll
+                for (int mf = 0; mf < 2; ++mf)
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf) {
+                        if (Bk)
+                            *reinterpret_cast<double2*>(Bk + (size_t)(b * 16 + mf * 8 + g) * STR + nf * 8 + 2 * t) =
+                                make_double2(acc[mf][nf][0], acc[mf][nf][1]);
+                        colsq[nf][0] = fma(acc[mf][nf][0], acc[mf][nf][0], colsq[nf][0]);
+                        colsq[nf][1] = fma(acc[mf][nf][1], acc[mf][nf][1], colsq[nf][1]);
+                    }
+            }
+            double v[8];
+#pragma unroll
+            for (int nf = 0; nf < 4; ++nf) { v[2 * nf] = colsq[nf < NF ? nf : 0][0]; v[2 * nf + 1] = colsq[nf < NF ? nf : 0][1]; }
+            sq[(size_t)k * NT + (g >> 1) * 8 + 2 * t + (g & 1)] = reduce8_over_g(v, lane);
+        }
+        if (warp < MW) {   // this warp's slice of fmean^T [K x NT] = q_mu^T [K x Mp] * A tile (rows >= K of W_mT are zero)
+            double* mn = mnpart + ((size_t)buf * MW + warp) * K * NT;
+            double acc[2][NF][2];
+            zero_acc<NF>(acc);
+            const double* wm = ly.W_mT + (size_t)mkb0 * 32 + lane;
+            const double* tb = T + t * STR + g;
+            for (int kb = mkb0; kb < mkb1; kb += 2) {
+                const double a0 = __ldg(wm + (size_t)(kb - mkb0) * 32);
+                const double* tr0 = tb + (size_t)kb * 4 * STR;
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf) dmma(acc[0][nf], a0, tr0[nf * 8]);
+                if (kb + 1 < mkb1) {
+                    const double a1 = __ldg(wm + (size_t)(kb + 1 - mkb0) * 32);
+                    const double* tr1 = tb + (size_t)(kb + 1) * 4 * STR;
+#pragma unroll
+                    for (int nf = 0; nf < NF; ++nf) dmma(acc[1][nf], a1, tr1[nf * 8]);
+                }
+            }
+            if (g < K) {
+#pragma unroll
+                for (int nf = 0; nf < NF; ++nf)
+                    *reinterpret_cast<double2*>(mn + (size_t)g * NT + nf * 8 + 2 * t) =
+                        make_double2(acc[0][nf][0] + acc[1][nf][0], acc[0][nf][1] + acc[1][nf][1]);
+            }
+        }
+        {   // |a_n|^2 over this warp's share of the rows (lane = column)
+            double s0 = 0.0, s1 = 0.0;
+            for (int m = warp * (Mp / NW); m < (warp + 1) * (Mp / NW); m += 2) {
+                const double v0 = T[(size_t)m * STR + lane], v1 = T[(size_t)(m + 1) * STR + lane];
+                s0 = fma(v0, v0, s0); s1 = fma(v1, v1, s1);
+            }
+            aspart[((size_t)buf * NW + warp) * NT + lane] = s0 + s1;
+        }
+        __syncwarp();
+        unsigned last = 0;
+        if (lane == 0) last = mbar_arrive_pending(&done[buf]) == 1u;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {   // every warp has left the tile: fold the partial sums, then refill the buffer
+            mbar_wait(&done[buf], (unsigned)((i / NBUF) & 1));
+            const int64_t n0 = tile * NT;
+            const double* sqb = sqpart + (size_t)buf * NW * K * NT;
+            const double* mnb = mnpart + (size_t)buf * MW * K * NT;
+            double asq = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) asq += aspart[((size_t)buf * NW + w) * NT + lane];
+            for (int k = 0; k < K; ++k) {
+                double sv = 0.0, mv = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) sv += sqb[((size_t)w * K + k) * NT + lane];
+#pragma unroll
+                for (int w = 0; w < MW; ++w) mv += mnb[((size_t)w * K + k) * NT + lane];
+                cb.fvar[(size_t)(n0 + lane) * K + k] = (variance - asq) + sv;   // Knn - sum A^2 + sum LTA^2
+                cb.fmean[(size_t)(n0 + lane) * K + k] = mv;
+            }
+            __syncwarp();
+            if (lane == 0 && i + NBUF < my_tiles) issue(i + NBUF);
+        }
+    }
+}
+
+// ==================================================================================================
 // host side
 // ==================================================================================================
 bool cond_fwd_a_wants_pipe(int NT) { return NT == 32 && getenv("MGP_FWD_A_PIPE") != nullptr; }
@@ -447,6 +605,26 @@ void cond_fwd_fused(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln
     const int grid = persistent_grid(cond_fwd_fused_kernel<32>, threads, smem, ntiles, 0, ln);
     static const int dbg = getenv("MGP_FUSED_DBG") ? atoi(getenv("MGP_FUSED_DBG")) : 0;
     cond_fwd_fused_kernel<32><<<grid, threads, smem, ln.stream>>>(ly, cb, ntiles, dbg);
+    ln.tick();
+}
+
+static size_t fwd_b_16w_smem(const LayerDev& ly, int NT) {
+    return ((size_t)SK_BAR_DOUBLES + (size_t)2 * ly.Mp * (NT + 4) +
+            (size_t)2 * ((SK_WARPS_NT16 + SK_WARPS) * ly.K * NT + SK_WARPS_NT16 * NT)) * sizeof(double);
+}
+// even K (a warp's two consecutive passes balance), every warp needs a block (Mp >= 256), and the larger partial-sum
+// buffers must fit beside the two tiles
+bool cond_fwd_b_wants_16w(const LayerDev& ly, int NT) {
+    return NT == 32 && getenv("MGP_FWD_B_16W") != nullptr && ly.K % 2 == 0 && ly.Mp >= 256 &&
+           fwd_b_16w_smem(ly, NT) <= (size_t)227 * 1024;
+}
+
+void cond_fwd_b_16w(const LayerDev& ly, const ChunkBuffers& cb, const Launch& ln) {
+    const int NT = 32;
+    const int ntiles = (int)((cb.n + NT - 1) / NT);
+    const size_t smem16 = fwd_b_16w_smem(ly, NT);
+    const int grid = persistent_grid(cond_fwd_b16_kernel<32, 2>, SK_WARPS_NT16 * 32, smem16, ntiles, 0, ln);
+    cond_fwd_b16_kernel<32, 2><<<grid, SK_WARPS_NT16 * 32, smem16, ln.stream>>>(ly, cb, ntiles);
     ln.tick();
 }
 

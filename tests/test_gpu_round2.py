@@ -511,7 +511,7 @@ def test_fused_forward_kernel_matches_the_goldens(hg, monkeypatch):
 # the alternative forms of cond_fwd_a / cond_bwd_b (selectable for A/B timing) compute the same numbers
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("env", [{"MGP_NO_KUF_STASH": "1"}, {"MGP_FWD_A_PIPE": "1", "MGP_BWD_B_RING": "1"},
-                                 {"MGP_FWD_A_PIPE": "1", "MGP_NO_KUF_STASH": "1"}])
+                                 {"MGP_FWD_A_PIPE": "1", "MGP_NO_KUF_STASH": "1"}, {"MGP_FWD_B_16W": "1"}])
 def test_alternative_kernel_forms_agree(hg, monkeypatch, env):
     """Default: barrier-phased cond_fwd_a that keeps its Kuf tiles, two-CTA cond_bwd_b that reads them back.
     MGP_FWD_A_PIPE / MGP_BWD_B_RING select the one-CTA software-pipelined / ring forms (measured slower),
@@ -519,7 +519,8 @@ def test_alternative_kernel_forms_agree(hg, monkeypatch, env):
     of the E-sum accumulation differs."""
     from modulatedgps_b200 import _lib
     ctx = _lib.get_context()
-    cases = [_case(3000, 2, 256, 4, 16, seed=3000), _case(700, 5, 96, 3, 8, seed=7), _case(1500, 3, 400, 2, 4, seed=11)]
+    cases = [_case(3000, 2, 256, 4, 16, seed=3000), _case(700, 5, 96, 3, 8, seed=7), _case(1500, 3, 400, 2, 4, seed=11),
+             _case(900, 2, 324, 2, 4, seed=13)]
     for case, X, Y, z, u in cases:
         model = hg.build_model(case)
         e0, g0 = model.elbo_and_grads(X, Y, noise=(z, u))

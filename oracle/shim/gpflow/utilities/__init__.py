@@ -22,6 +22,11 @@ def to_default_int(x):
     return tf.cast(x, tf.int64)
 
 
+def parameter_dict(module):
+    """gpflow.utilities.parameter_dict: {'.path.to.parameter': Parameter} (keys carry GPflow's leading dot)."""
+    return {"." + k: p for k, p in module.parameters_dict.items()}
+
+
 def print_summary(module, fmt=None):
     for k, p in module.parameters_dict.items():
         print(f"{k:50s} {type(p.transform).__name__:18s} trainable={p.trainable} shape={tuple(p.shape)}")

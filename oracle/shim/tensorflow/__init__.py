@@ -398,7 +398,10 @@ class GradientTape:
             g = [_t(output_gradients) if tgt is _t(s) or tgt.data_ptr() == _t(s).data_ptr() else None for s in srcs]
         else:
             go = None if output_gradients is None else _t(output_gradients)
-            g = _torch.autograd.grad(tgt, [_t(s) for s in srcs], grad_outputs=go, retain_graph=True, allow_unused=True)
+            # (a source that already is a torch tensor is passed AS IS: re-wrapping it makes an alias that is not the
+            #  leaf the graph was recorded on)
+            src_t = [s if isinstance(s, _torch.Tensor) else _t(s) for s in srcs]
+            g = _torch.autograd.grad(tgt, src_t, grad_outputs=go, retain_graph=True, allow_unused=True)
         g = [None if e is None else _wrap(e) for e in g]
         return g[0] if single else g
 

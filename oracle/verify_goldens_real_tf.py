@@ -8,6 +8,7 @@ stand-in for that stack (oracle/shim, oracle/run_reference.py), so the third-par
 restatement (SURVEY.md §8c, Appendix A "[3P-memory]").  On a machine that has the real stack this script closes that gap:
 
     python oracle/verify_goldens_real_tf.py /path/to/ModulatedGPs [golden-name ...]
+    python oracle/verify_goldens_real_tf.py --shim /root/reference [golden-name ...]     # self-test of this script on the stand-ins
 
 For every fixture it rebuilds the reference model from the fixture's constrained parameter values, serves the fixture's
 explicit noise to the two places the reference draws randomness — tf.random.normal (models.py:57,98) and TFP's uniform
@@ -134,6 +135,11 @@ def relerr(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), np.finfo(np.float64).tiny)) if b.size else 0.0
 
 
+def to_np(x):
+    """EagerTensor -> numpy (the stand-ins' tensors are torch tensors that may carry a graph)."""
+    return x.detach().numpy() if hasattr(x, "detach") else x.numpy()
+
+
 def evaluate(tf, gpflow, noise, case, g):
     model = build_model(case)
     z, u = g["z"], g["u"]
@@ -145,7 +151,7 @@ def evaluate(tf, gpflow, noise, case, g):
         loss = model._training_loss((g["X"], g["Y"]))
     assert not noise.queue, "the reference consumed less noise than supplied"
     grads = tape.gradient(loss, variables)
-    out = {"elbo": -float(loss.numpy())}
+    out = {"elbo": -float(to_np(loss))}
     by_var = {id(p.unconstrained_variable): golden_key(path, case)
               for path, p in gpflow.utilities.parameter_dict(model).items() if p.trainable}
     # the likelihood variances are shared objects reached through several module paths: name them by
@@ -160,15 +166,15 @@ def evaluate(tf, gpflow, noise, case, g):
     if av is not None and av is not pv:
         by_var[id(av.unconstrained_variable)] = "assign_lik_var"
     for v, gr in zip(variables, grads):
-        out["gradu." + by_var[id(v)]] = np.zeros(v.shape) if gr is None else -gr.numpy()
+        out["gradu." + by_var[id(v)]] = np.zeros(tuple(v.shape)) if gr is None else -to_np(gr)
     Xtest = g["Xtest"]
     my, vy = model.predict_y(Xtest, S=2)
-    out["predict_y.mean"], out["predict_y.var"] = my[0].numpy(), vy[0].numpy()
+    out["predict_y.mean"], out["predict_y.var"] = to_np(my[0]), to_np(vy[0])
     Xt1 = model.integrate(Xtest, 1)[0]
     for name, layer in (("pred", model.pred_layer), ("assign", model.assign_layer)):
         fm, fv = layer.predict_f(Xt1, full_cov=False)
-        out[f"predict_f.{name}.mean"], out[f"predict_f.{name}.var"] = fm[0].numpy(), fv[0].numpy()
-    pa = model.predict_assign(Xtest, S=3).numpy()
+        out[f"predict_f.{name}.mean"], out[f"predict_f.{name}.var"] = to_np(fm[0]), to_np(fv[0])
+    pa = to_np(model.predict_assign(Xtest, S=3))
     out["predict_assign.probs"], out["predict_assign.argmax"] = pa, np.argmax(pa, 1).astype(np.int64)
     if "sample.z_assign" in g:
         za, us, zp = g["sample.z_assign"], g["sample.u"], g["sample.z_pred"]
@@ -177,11 +183,27 @@ def evaluate(tf, gpflow, noise, case, g):
         noise.push(za, us.reshape(1, S2 * Nt, K), zp)          # order: models.py:57 (W_dist), :95, :98
         sy, sf = model.predict_samples(Xtest, S=S2)
         assert not noise.queue
-        out["predict_samples.y"], out["predict_samples.f"] = sy.numpy(), sf.numpy()
+        out["predict_samples.y"], out["predict_samples.f"] = to_np(sy), to_np(sf)
     return out
 
 
+class ShimNoise:
+    """--shim self-test: the stand-ins draw from their own queue (tf._noise); same interface as NoiseQueue."""
+
+    def __init__(self, tf):
+        self.tf = tf
+
+    @property
+    def queue(self):
+        return self.tf._noise.queue
+
+    def push(self, *arrays):
+        self.tf._noise.push(*arrays)
+
+
 def main(argv):
+    shim = "--shim" in argv
+    argv = [a for a in argv if a != "--shim"]
     if len(argv) < 2:
         print(__doc__)
         return 2
@@ -189,21 +211,30 @@ def main(argv):
     if not os.path.isdir(os.path.join(ref_root, "MixtureGPs")):
         raise SystemExit(f"{ref_root} is not a checkout of LouieMiddle/ModulatedGPs (no MixtureGPs/)")
     sys.path.insert(0, ref_root)
+    if shim:
+        # self-test of THIS script's logic (model construction, noise order, gradient naming, comparisons) on the
+        # stand-ins that produced the goldens: must report agreement to the last digit.  Proves nothing about GPflow.
+        sys.path.insert(0, os.path.join(HERE, "shim"))
     import tensorflow as tf
     import tensorflow_probability as tfp
     import gpflow
-    for mod in (tf, gpflow):
-        if "oracle/shim" in (mod.__file__ or "").replace("\\", "/"):
-            raise SystemExit("the torch-backed stand-in is on the path: this script needs the REAL TensorFlow / GPflow")
-    print(f"tensorflow {tf.__version__}, gpflow {gpflow.__version__}, tensorflow-probability {tfp.__version__} "
-          "(pinned: 2.10.1 / 2.7.0 / 0.18.0)")
-    src = inspect.getsource(gpflow.likelihoods.RobustMax.prob_is_largest)
-    print("gpflow RobustMax.prob_is_largest squashes its CDFs with:")
-    for line in src.splitlines():
-        if "cdfs" in line and "*" in line and "+" in line:
-            print("    " + line.strip() + "        <- include/mgp.h ships MGP_ROBUSTMAX_CDF_SQUASH = 1e-4")
-    noise = NoiseQueue()
-    patch_noise(tf, tfp, noise)
+    on_shim = any("oracle/shim" in (mod.__file__ or "").replace("\\", "/") for mod in (tf, gpflow))
+    if on_shim != shim:
+        raise SystemExit("the torch-backed stand-in is on the path: this script needs the REAL TensorFlow / GPflow"
+                         if on_shim else "--shim given but a real TensorFlow / GPflow was imported")
+    if shim:
+        print("SELF-TEST on the torch-backed stand-ins (oracle/shim): checks this script, not GPflow")
+        noise = ShimNoise(tf)
+    else:
+        print(f"tensorflow {tf.__version__}, gpflow {gpflow.__version__}, tensorflow-probability {tfp.__version__} "
+              "(pinned: 2.10.1 / 2.7.0 / 0.18.0)")
+        src = inspect.getsource(gpflow.likelihoods.RobustMax.prob_is_largest)
+        print("gpflow RobustMax.prob_is_largest squashes its CDFs with:")
+        for line in src.splitlines():
+            if "cdfs" in line and "*" in line and "+" in line:
+                print("    " + line.strip() + "        <- include/mgp.h ships MGP_ROBUSTMAX_CDF_SQUASH = 1e-4")
+        noise = NoiseQueue()
+        patch_noise(tf, tfp, noise)
     names = argv[2:] or sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
                                if not os.path.basename(p).startswith("hp_"))
     worst_all, failed = 0.0, []
@@ -228,7 +259,8 @@ def main(argv):
         if not ok:
             failed.append(name)
         print(f"{name:48s} worst rel. err. {worst:9.2e} ({where})  {'ok' if ok else 'MISMATCH'}")
-    print(f"{len(names) - len(failed)} / {len(names)} fixtures agree with the real reference at {RTOL:g}; worst {worst_all:.2e}")
+    print(f"{len(names) - len(failed)} / {len(names)} fixtures agree with the {'stand-ins (self-test)' if shim else 'real reference'} "
+          f"at {RTOL:g}; worst {worst_all:.2e}")
     return 1 if failed else 0
 
 

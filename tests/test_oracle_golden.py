@@ -2,6 +2,7 @@
 the reference's own MixtureGPs code on the TF/GPflow shim (tests/golden/make_golden.py), the analytic
 known-answer ELBO, invariants from SURVEY.md §4, and float64 finite differences."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -163,3 +164,20 @@ def test_gradients_against_central_finite_differences():
         fd = (vals[0] - vals[1]) / (2 * h)
         an = float(grads[f"{lname}.{key}"][idx])
         assert abs(fd - an) <= tol * max(1.0, abs(an)), (lname, key, fd, an)
+
+
+def test_real_tf_verifier_script_reproduces_the_goldens_on_the_stand_ins():
+    """oracle/verify_goldens_real_tf.py is meant for a machine with the pinned TensorFlow / GPflow / TFP (it cannot run
+    here).  Its own logic — model construction from a fixture, the order in which the noise is served, the naming of the
+    gradients, the comparisons — is checked by running it in --shim mode on the stand-ins that produced the goldens: every
+    stored output must come back to the last digit."""
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/MixtureGPs"):
+        pytest.skip("/root/reference is mounted in the authoring container only")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "oracle", "verify_goldens_real_tf.py"), "--shim", "/root/reference",
+                        "demo_tf2.pert", "demo_tf2_2d_modified_multiclass.pert", "smgpmod_gauss_small.pert"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "3 / 3 fixtures agree" in r.stdout and "worst 0.00e+00" in r.stdout, r.stdout

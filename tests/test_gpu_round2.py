@@ -581,3 +581,33 @@ def test_config5_parity_on_the_16k_point_subsample():
         mine = grads[k].cpu().numpy().reshape(r.shape)
         t = tol[k.split(".")[0]] if "." in k else max(tol.values())
         assert relerr(mine, r) <= t, (k, relerr(mine, r), t)
+
+
+def test_config4_parity_on_a_64k_point_subsample():
+    """config #4 AS BENCHMARKED (D = 2, M = 256, K = 4, S = 16; jittered-grid Z, assign lengthscale 1.5:
+    cond(Kuu) = 3e6), 65536 points with explicit noise, ELBO and every gradient against the CPU oracle; the bound is
+    max(1e-9, 100 eps cond) per layer."""
+    from modulatedgps_b200 import _lib, workloads as W
+    from oracle import svgp_mixture as O
+    n = 1 << 16
+    case, X, Y = W.config4_workload(n, seed=0, num_data=n)
+    K, S = case["K"], case["S"]
+    rng = np.random.default_rng(3)
+    z = rng.standard_normal((S, n, K))
+    u = rng.uniform(np.finfo(np.float64).tiny, 1.0, (S, n, K))
+    model = W.model_from_case(case)
+    elbo, grads = model.elbo_and_grads(X, Y, noise=(z, u))
+    _lib.get_context().check_status()
+    ref, rg = O.elbo_and_grads(case["model"], case["lik"], O.layer_from_numpy(case["pred"]), O.layer_from_numpy(case["assign"]),
+                               O.as_t(case["lik_var"]), None, X, Y, z, u, case["num_data"])
+    eps = np.finfo(np.float64).eps
+    tol = {name: max(RTOL, 100 * eps * float(np.linalg.cond(O.kuu(O.layer_from_numpy(case[name])).numpy())))
+           for name in ("pred", "assign")}
+    assert abs(float(elbo) - ref) <= RTOL * abs(ref)
+    worst = {}
+    for k, r in rg.items():
+        mine = grads[k].cpu().numpy().reshape(r.shape)
+        t = tol[k.split(".")[0]] if "." in k else max(tol.values())
+        worst[k] = relerr(mine, r)
+        assert worst[k] <= t, (k, worst[k], t)
+    print("config #4, 64K points: worst gradient rel. err.", max(worst.values()), worst)

@@ -150,6 +150,19 @@ def load_reference_dataset(name: str, seed: int = 0):
         return dataset_utils.load_toy_multimodal_data(rng)           # dataset_utils.py:100-114
     if name == "toy_2d_categorical":
         return dataset_utils.load_toy_2d_data_categorical(rng)       # dataset_utils.py:149-165
+    if name == "toy_2d":
+        return dataset_utils.load_toy_2d_data(rng)                   # dataset_utils.py:128-146 (demo_tf2_2d.py:22)
+    if name == "toy_categorical":
+        return dataset_utils.load_toy_data_categorical(rng)          # dataset_utils.py:83-97 (demo_tf2_modified_multiclass.py:22)
+    if name == "john_doe_boundary":
+        cwd = os.getcwd()
+        os.chdir(os.path.join(REFERENCE_ROOT, "demos"))              # loader reads "../data/..." (dataset_utils.py:43)
+        try:
+            np.random.seed(seed)   # train_test_split has no random_state (dataset_utils.py:76): pin the global RNG
+            n, Xtr, Ytr, Xte, _ = dataset_utils.load_john_doe()      # demo_john_doe_multi_class.py:23
+        finally:
+            os.chdir(cwd)
+        return n, Xtr.astype(np.float64), Ytr.astype(np.float64), Xte.astype(np.float64)
     if name == "john_doe_runs":
         cwd = os.getcwd()
         os.chdir(os.path.join(REFERENCE_ROOT, "demos"))              # loader reads "../data/..." (dataset_utils.py:10)

@@ -82,6 +82,19 @@ def test_demo_multiclass_reaches_the_published_elbo_with_either_squash():
     assert -1.6 <= at[400] <= -0.8 and max(a["elbos"][: 1300 // 5]) > 0.0
 
 
+@pytest.mark.parametrize("demo", ["tf2_2d", "tf2_modified", "tf2_modified_multiclass", "john_doe_multi_class"])
+def test_the_other_four_demos_follow_their_published_curves(demo):
+    """The reference's demos outside BASELINE.json's three configs (demos/demo_tf2_2d.py, demo_tf2_modified.py,
+    demo_tf2_modified_multiclass.py, demo_john_doe_multi_class.py), replayed from the reference's own data sets and k-means
+    centroids (tests/golden/datasets/demo_datasets.npz) and checked against the ELBO curves of final_figs/: first log,
+    the early / plateau part of the curve point by point, and the level reached (best running median over 100 logs — the
+    end level itself is chaotic in the last bit, see the john_doe test).  Two of them train SMGPModified with MultiClass
+    experts, i.e. two more published trajectories through the RobustMax path."""
+    rec, anchors = _run(demo)
+    _check(rec, dict(anchors, final_at_least=-np.inf))
+    assert _peak_running_median(rec["elbos"]) >= anchors["final_at_least"], rec["summary"]
+
+
 def _peak_running_median(e, width=100):
     e = np.asarray(e)
     return max(float(np.median(e[a:a + width])) for a in range(0, len(e) - width + 1, width // 2))

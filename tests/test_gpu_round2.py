@@ -611,3 +611,35 @@ def test_config4_parity_on_a_64k_point_subsample():
         worst[k] = relerr(mine, r)
         assert worst[k] <= t, (k, worst[k], t)
     print("config #4, 64K points: worst gradient rel. err.", max(worst.values()), worst)
+
+
+def test_survey_invariants_hold_on_the_cuda_path(hg):
+    """SURVEY.md §4's invariants, on the kernels (tests/test_oracle_golden.py checks them on the oracle):
+    predict_y variance = predict_f variance + sigma^2_k (likelihoods.py:32); predict_assign rows sum to 1 (models.py:88);
+    the ELBO's data term is a per-point MEAN — duplicating the minibatch (and its noise) leaves it unchanged — while the KL
+    term scales with 1 / num_data only (models.py:76,79); the data term does not depend on S when all S samples are equal."""
+    case, g = load_golden("demo_john_doe.pert")
+    model = hg.build_model(case)
+    Xt = g["Xtest"]
+    fm, fv = model.pred_layer.predict_f(Xt)
+    my, vy = model.predict_y(Xt, S=1)
+    lik_var = np.asarray(case["lik_var"]).reshape(1, -1)
+    assert relerr(np.asarray(vy[0]) - np.asarray(fv), np.broadcast_to(lik_var, np.asarray(fv).shape)) <= 1e-12
+    assert relerr(np.asarray(my[0]), np.asarray(fm)) <= 1e-14
+    assert np.allclose(np.asarray(model.predict_assign(Xt)).sum(1), 1.0, atol=1e-14)
+    X, Y, z, u = g["X"], g["Y"], g["z"], g["u"]
+    kl = float(model.pred_layer.prior_kl()) + float(model.assign_layer.prior_kl())
+    e1, _ = model.elbo_and_grads(X, Y, noise=(z, u))
+    X2, Y2 = np.concatenate([X, X]), np.concatenate([Y, Y])
+    z2, u2 = np.concatenate([z, z], 1), np.concatenate([u, u], 1)
+    e2, _ = model.elbo_and_grads(X2, Y2, noise=(z2, u2))
+    assert abs(float(e1) - float(e2)) <= 1e-12 * abs(float(e1))          # mean over points; KL / num_data unchanged
+    data_term = float(e1) + kl / case["num_data"]
+    case10 = dict(case, num_data=10.0 * case["num_data"])
+    e10, _ = hg.build_model(case10).elbo_and_grads(X, Y, noise=(z, u))
+    assert abs(float(e10) - (data_term - kl / case10["num_data"])) <= 1e-12 * abs(float(e10))
+    zs, us = np.repeat(z[:1], 5, 0), np.repeat(u[:1], 5, 0)               # five identical samples == one sample
+    case5, case1s = dict(case, S=5), dict(case, S=1)
+    e5, _ = hg.build_model(case5).elbo_and_grads(X, Y, noise=(zs, us))
+    e1s, _ = hg.build_model(case1s).elbo_and_grads(X, Y, noise=(z[:1], u[:1]))
+    assert abs(float(e5) - float(e1s)) <= 1e-12 * abs(float(e1s))

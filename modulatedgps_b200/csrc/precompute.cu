@@ -7,6 +7,7 @@
 //   KL             gpflow gauss_kl, whitened                           (call site models.py:79)
 //   backward       TF autodiff of the above                            (utils/training_utils.py:8-10)
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "exp_tab.h"
@@ -74,13 +75,19 @@ __global__ void kuu_kernel(LayerDev ly) {
 //       the panel and for trinv_kernel (`Dinv`, [Mp/32][32][32])
 //   (2) panel: P <- P V^T on DMMA, one 8-row block per warp step (was: one row per thread, a 528-FMA dependent chain
 //       per row — the longest phase of a panel step)
-//   (3) trailing update on DMMA, one 32x32 tile per warp
+//   (3) trailing update on DMMA, one 32x32 tile per warp.  The panel's rows come from a shared-memory copy the panel
+//       phase leaves behind ([rows][36]: conflict-free 256-byte fragment reads) whenever it fits (Mp <= ~700): read from
+//       global memory, a fragment load touches 8 cache lines and the update spent as many L1 wavefronts as DMMA clocks
+//       (16 k clocks per round of 16 tiles for 8.2 k of DMMA).
 // The diagonal blocks' explicit inverses cost cond(D) eps <= cond(L) eps in the panel, the same order as the explicit
 // L^-1 every consumer of this factor uses anyway.
 // --------------------------------------------------------------------------------------------------
 constexpr int CHOL_THREADS = 512;
 
+constexpr int CHOL_PSTR = 36;   // row stride of the shared-memory panel copy (== 4 mod 16 doubles)
+template <bool panel_in_smem>
 __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_kernel(double* L, double* Dinv, int Mp, int* status) {
+    extern __shared__ __align__(16) double Ps[];   // [Mp - 32][CHOL_PSTR] panel rows below the diagonal block (panel_in_smem)
     __shared__ double Dg[32][33];
     __shared__ double Vg[32][36];   // row stride == 4 mod 16 doubles: conflict-free B-fragment reads
     __shared__ double invd[32];     // 1 / D[r][r]
@@ -157,6 +164,8 @@ __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_kernel(double* L, double
             for (int ni = 0; ni < 4; ++ni) {
                 rowp[ni * 8 + 2 * t] = acc[ni][0];
                 rowp[ni * 8 + 2 * t + 1] = acc[ni][1];
+                if (panel_in_smem)
+                    *reinterpret_cast<double2*>(Ps + (size_t)(u * 8 + g) * CHOL_PSTR + ni * 8 + 2 * t) = make_double2(acc[ni][0], acc[ni][1]);
             }
         }
         __syncthreads();
@@ -173,6 +182,22 @@ __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_kernel(double* L, double
             for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                 for (int ni = 0; ni < 4; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+            if (panel_in_smem) {
+                const double* pa = Ps + (size_t)(ti * 32 + g) * CHOL_PSTR + t;
+                const double* pb = Ps + (size_t)(tj * 32 + g) * CHOL_PSTR + t;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    double a[4], b[4];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi) a[mi] = pa[mi * 8 * CHOL_PSTR + kk * 4];
+#pragma unroll
+                    for (int ni = 0; ni < 4; ++ni) b[ni] = pb[ni * 8 * CHOL_PSTR + kk * 4];
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                        for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni], a[mi], b[ni]);
+                }
+            } else {
 #pragma unroll 4
             for (int kk = 0; kk < 8; ++kk) {
                 double a[4], b[4];
@@ -184,6 +209,7 @@ __global__ void __launch_bounds__(CHOL_THREADS, 1) chol_kernel(double* L, double
                 for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                     for (int ni = 0; ni < 4; ++ni) dmma(acc[mi][ni], a[mi], b[ni]);
+            }
             }
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi)
@@ -343,7 +369,16 @@ void precompute_chol(const LayerDev& ly, bool need_bwd, int* d_status, const Lau
     kuu_kernel<<<(unsigned)((mm + 255) / 256), 256, 0, ln.stream>>>(ly);
     ln.tick(2);
     cudaMemcpyAsync(ly.L, ly.Kuu, sizeof(double) * mm, cudaMemcpyDeviceToDevice, ln.stream);
-    chol_kernel<<<1, CHOL_THREADS, 0, ln.stream>>>(ly.L, ly.Dinv, Mp, d_status);
+    {
+        const size_t panel_bytes = (size_t)(Mp - 32) * CHOL_PSTR * sizeof(double);
+        const int panel_in_smem = panel_bytes <= (size_t)200 * 1024 && getenv("MGP_CHOL_PANEL_GLOBAL") == nullptr;
+        if (panel_in_smem) {
+            cudaFuncSetAttribute(chol_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel_bytes);
+            chol_kernel<true><<<1, CHOL_THREADS, panel_bytes, ln.stream>>>(ly.L, ly.Dinv, Mp, d_status);
+        } else {
+            chol_kernel<false><<<1, CHOL_THREADS, 0, ln.stream>>>(ly.L, ly.Dinv, Mp, d_status);
+        }
+    }
     cudaMemsetAsync(ly.Linv, 0, sizeof(double) * mm, ln.stream);
     cudaFuncSetAttribute(trinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TI_SMEM_DOUBLES * sizeof(double)));
     trinv_kernel<<<Mp / 32, TI_WARPS * 32, TI_SMEM_DOUBLES * sizeof(double), ln.stream>>>(ly.L, ly.Dinv, ly.Linv, Mp);

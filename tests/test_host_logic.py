@@ -243,3 +243,27 @@ def test_oracle_conditional_against_60_digit_arithmetic():
     assert 1e6 < cond < 1e7
     floor = np.finfo(np.float64).eps * cond
     assert relerr(fm.numpy(), d["fmean"]) <= floor and relerr(fv.numpy(), d["fvar"]) <= floor
+
+
+def test_reference_arm_prints_the_contract_line_and_other_ranks_stay_silent():
+    """`bench.py --impl reference` (the CPU arm the driver launches beside the GPU arm): ONE JSON line on rank 0 with the
+    same metric / unit / config as the native arm, `impl`, `cpu_baseline` and a zero-copy `e2e`; ranks > 0 exit 0 without
+    output.  Run on a reduced point count so that it takes seconds."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"]
+    env = dict(os.environ, RANK="0")
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "elbo_fwd_bwd_points_per_s" and d["unit"] == "points/s"
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["higher_is_better"] is True and d["dtype"] == "f64"
+    assert d["config"]["N"] == 1 << 20 and d["config"]["M"] == 256 and d["config"]["K"] == 4 and d["config"]["S"] == 16
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["value"] > 0 and abs(d["value"] - 8192 / (d["ms_per_step"] * 1e-3)) <= 1e-6 * d["value"]
+    silent = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, RANK="1"), timeout=600)
+    assert silent.returncode == 0 and silent.stdout.strip() == ""
